@@ -1,0 +1,179 @@
+// api.cu — context, memory and timing entry points of libjsdrcuda.so.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace jsdr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace jsdr
+
+using namespace jsdr;
+
+extern "C" int jsdr_abi_version(void) { return JSDR_ABI_VERSION; }
+
+extern "C" const char *jsdr_last_error(void) { return g_err; }
+
+extern "C" int jsdr_device_count(int *count)
+{
+    JSDR_REQUIRE(count, JSDR_EINVAL, "null argument");
+    *count = 0;
+    JSDR_CUDA(cudaGetDeviceCount(count));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
+{
+    JSDR_REQUIRE(out, JSDR_EINVAL, "null argument");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        // no CPU fallback by design: the product path is the CUDA path
+        set_error("jsdr_ctx_create: no CUDA device (%s)", cudaGetErrorString(e));
+        return JSDR_ECUDA;
+    }
+    JSDR_REQUIRE(device >= 0 && device < count, JSDR_EINVAL, "device index out of range");
+    JSDR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    JSDR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("jsdr_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                  device, prop.major, prop.minor);
+        return JSDR_EUNSUPPORTED;
+    }
+    jsdr_ctx *ctx = new jsdr_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    JSDR_CUDA(cudaEventCreate(&ctx->ev_t0));
+    JSDR_CUDA(cudaEventCreate(&ctx->ev_t1));
+    JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    *out = ctx;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
+{
+    if (!ctx) return JSDR_OK;
+    ctx->bind();
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side);
+    cudaEventDestroy(ctx->ev_t0);
+    cudaEventDestroy(ctx->ev_t1);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->side);
+    delete ctx;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
+{
+    JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaStreamSynchronize(ctx->side));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count)
+{
+    JSDR_REQUIRE(ctx && count, JSDR_EINVAL, "null argument");
+    *count = ctx->launches;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_host_alloc(jsdr_ctx *ctx, size_t bytes, void **out)
+{
+    JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_host_free(jsdr_ctx *ctx, void *p)
+{
+    JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    if (p) JSDR_CUDA(cudaFreeHost(p));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_dev_alloc(jsdr_ctx *ctx, size_t bytes, void **out)
+{
+    JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        set_error("jsdr_dev_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? JSDR_ENOMEM : JSDR_ECUDA;
+    }
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_dev_free(jsdr_ctx *ctx, void *p)
+{
+    JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    if (p) JSDR_CUDA(cudaFree(p));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_memcpy_h2d(jsdr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    JSDR_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_memcpy_d2h(jsdr_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    JSDR_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_memset_dev(jsdr_ctx *ctx, void *dst_dev, int value, size_t bytes)
+{
+    JSDR_REQUIRE(ctx && dst_dev, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_timer_start(jsdr_ctx *ctx)
+{
+    JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_timer_stop_ms(jsdr_ctx *ctx, float *ms)
+{
+    JSDR_REQUIRE(ctx && ms, JSDR_EINVAL, "null argument");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    JSDR_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    JSDR_CUDA(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return JSDR_OK;
+}

@@ -1,0 +1,100 @@
+// common.cuh — shared plumbing for libjsdrcuda.so (context, error reporting,
+// streaming load/store helpers).  sm_100a only; there is no CPU fallback.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/jsdrcuda.h"
+
+namespace jsdr {
+
+void set_error(const char *fmt, ...);
+
+#define JSDR_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            jsdr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,             \
+                            cudaGetErrorString(_e));                                 \
+            return JSDR_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+#define JSDR_REQUIRE(cond, code, msg)                                                \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            jsdr::set_error("%s: %s", __func__, msg);                                \
+            return code;                                                             \
+        }                                                                            \
+    } while (0)
+
+#define JSDR_TRY(expr)                                                               \
+    do {                                                                             \
+        int _rc = (expr);                                                            \
+        if (_rc != JSDR_OK) return _rc;                                              \
+    } while (0)
+
+}  // namespace jsdr
+
+struct jsdr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;   // main stream: data kernels
+    cudaStream_t side = nullptr;     // side stream: data-independent phase scouts
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int64_t launches = 0;
+
+    int bind() const { return cudaSetDevice(device) == cudaSuccess ? JSDR_OK : JSDR_ECUDA; }
+};
+
+namespace jsdr {
+
+// Check the launch that was just made and count it.
+static inline int launched(jsdr_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return JSDR_ECUDA;
+    }
+    ctx->launches++;
+    return JSDR_OK;
+}
+
+// ---- device helpers -------------------------------------------------------
+#ifdef __CUDACC__
+// streaming (read-once) global loads: bypass L1 allocation
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f32(float *p, float v)
+{
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+__device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v)
+{
+    asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y));
+}
+#endif
+
+}  // namespace jsdr

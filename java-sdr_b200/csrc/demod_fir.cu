@@ -1,0 +1,542 @@
+// demod_fir.cu — the FIR + NCO parts of demod.java (:341-434) and the four
+// arithmetic methods of fir.java (:169-228), batched over channels.
+//
+// demod.java works in binary32 with a multiply and an add rounded separately
+// per tap (filter(), :385-389) and a float phase accumulator (:424-429);
+// __fmul_rn/__fadd_rn keep that order and never contract.  fir.java multiplies int
+// samples by double taps and truncates the double sum to int (:202-210).
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "handles.h"
+
+namespace jsdr {
+namespace dsp {
+
+constexpr int kChunk = 32;          // samples between NCO phase checkpoints
+constexpr int kTile = 1024;         // samples per CTA
+constexpr int kThreads = 256;
+constexpr int kTaps = 21, kHist = 20;
+
+// ------------------------------------------------------------------ demod.java
+// car is a sequential float accumulator (:427-429), data independent: replay it
+// once per channel and leave the value seen by every kChunk-th sample.
+__global__ void k_car_scout(const float *__restrict__ phi_, float *__restrict__ car_,
+                            float *__restrict__ chunk_car, int nchan, int S)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchan) return;
+    float car = car_[ch];
+    const float phi = phi_[ch];
+    const float twopi = (float)(2 * M_PI);
+    int nchunks = (S + kChunk - 1) / kChunk;
+    for (int c = 0; c < nchunks; c++) {
+        chunk_car[(size_t)c * nchan + ch] = car;
+        int steps = min(kChunk, S - c * kChunk);
+        for (int s = 0; s < steps; s++) {
+            car = __fsub_rn(car, phi);
+            if (car < 0.0f) car = __fadd_rn(car, twopi);
+        }
+    }
+    car_[ch] = car;
+}
+
+struct DemodParams {
+    const float2 *in;
+    long long chan_stride;
+    int S, nchan;
+    const float *w;            // [nchan][21]
+    const float *phi;
+    const float *chunk_car;
+    const float2 *hist_in;     // [nchan][20], entry k is local sample k-20
+    float2 *hist_out;
+    float2 *out;               // [nchan][S]
+    int dofir, dodwn;
+};
+
+__global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
+{
+    __shared__ float2 sX[kTile + kHist];
+    __shared__ float sCar[kTile + kTile / kChunk];
+    __shared__ float sW[kTaps];
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int t0 = blockIdx.x * kTile;
+    const int cnt = min(kTile, p.S - t0);
+    const float2 *src = p.in + (long long)ch * p.chan_stride;
+    if (tid < kTaps) sW[tid] = p.w[ch * kTaps + tid];
+    for (int i = tid; i < cnt + kHist; i += kThreads) {
+        int n = t0 - kHist + i;
+        sX[i] = (n < 0) ? p.hist_in[(size_t)ch * kHist + kHist + n] : src[n];
+    }
+    if (p.dodwn) {
+        // one thread per checkpoint chunk replays car (:427-429); padded so lanes
+        // (32 samples apart) do not share a bank
+        const float phi = p.phi[ch];
+        const float twopi = (float)(2 * M_PI);
+        const int nch = (cnt + kChunk - 1) / kChunk;
+        if (tid < nch) {
+            float car = p.chunk_car[(size_t)(t0 / kChunk + tid) * p.nchan + ch];
+            int steps = min(kChunk, cnt - tid * kChunk);
+            for (int s = 0; s < steps; s++) {
+                sCar[tid * (kChunk + 1) + s] = car;        // value used by this sample (:425-426)
+                car = __fsub_rn(car, phi);
+                if (car < 0.0f) car = __fadd_rn(car, twopi);
+            }
+        }
+    }
+    __syncthreads();
+    float2 *dst = p.out + (size_t)ch * p.S + t0;
+    for (int i = tid; i < cnt; i += kThreads) {
+        float si, sq;
+        if (p.dofir) {
+            // filter() :385-389 — newest sample first, w[0..20]
+            float oi = 0.0f, oq = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kTaps; k++) {
+                float2 x = sX[i + kHist - k];
+                oi = __fadd_rn(oi, __fmul_rn(x.x, sW[k]));
+                oq = __fadd_rn(oq, __fmul_rn(x.y, sW[k]));
+            }
+            si = oi;
+            sq = oq;
+        } else {
+            si = sX[i + kHist].x;
+            sq = sX[i + kHist].y;
+        }
+        if (p.dodwn) {
+            float car = sCar[(i / kChunk) * (kChunk + 1) + (i % kChunk)];
+            float ci = (float)cos((double)car);            // :425
+            float cq = (float)sin((double)car);            // :426
+            float a = si, b = sq;
+            si = __fsub_rn(__fmul_rn(a, ci), __fmul_rn(b, cq));   // :432
+            sq = __fadd_rn(__fmul_rn(a, cq), __fmul_rn(b, ci));   // :433
+        }
+        dst[i] = make_float2(si, sq);
+    }
+}
+
+__global__ void k_demod_tail(const DemodParams p)
+{
+    const int ch = blockIdx.x, k = threadIdx.x;
+    if (k >= kHist) return;
+    const float2 *src = p.in + (long long)ch * p.chan_stride;
+    int n = p.S - kHist + k;
+    p.hist_out[(size_t)ch * kHist + k] = (n < 0) ? p.hist_in[(size_t)ch * kHist + k + p.S] : src[n];
+}
+
+// ------------------------------------------------------------------ fir.java
+struct FirParams {
+    const int32_t *in;
+    long long chan_stride;
+    int S;
+    const double *w;           // [nchan][21]
+    const int32_t *hist_in;    // [nchan][20]
+    int32_t *hist_out;
+    int32_t *out;              // [nchan][S]
+};
+
+__global__ void __launch_bounds__(kThreads) k_fir_i32(const FirParams p)
+{
+    __shared__ int32_t sX[kThreads + kHist];
+    __shared__ double sW[kTaps];
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int t0 = blockIdx.x * kThreads;
+    const int cnt = min(kThreads, p.S - t0);
+    const int32_t *src = p.in + (long long)ch * p.chan_stride;
+    if (tid < kTaps) sW[tid] = p.w[ch * kTaps + tid];
+    for (int i = tid; i < cnt + kHist; i += kThreads) {
+        int n = t0 - kHist + i;
+        sX[i] = (n < 0) ? p.hist_in[(size_t)ch * kHist + kHist + n] : src[n];
+    }
+    __syncthreads();
+    if (tid < cnt) {
+        double o = 0.0;                                    // :202-206
+#pragma unroll
+        for (int k = 0; k < kTaps; k++) o = __dadd_rn(o, __dmul_rn((double)sX[tid + kHist - k], sW[k]));
+        // :210 (int)o — truncation toward zero, saturating, NaN -> 0 (cvt.rzi.s32.f64 does exactly that)
+        p.out[(size_t)ch * p.S + t0 + tid] = __double2int_rz(o);
+    }
+}
+
+__global__ void k_fir_tail(const FirParams p)
+{
+    const int ch = blockIdx.x, k = threadIdx.x;
+    if (k >= kHist) return;
+    const int32_t *src = p.in + (long long)ch * p.chan_stride;
+    int n = p.S - kHist + k;
+    p.hist_out[(size_t)ch * kHist + k] = (n < 0) ? p.hist_in[(size_t)ch * kHist + k + p.S] : src[n];
+}
+
+// complex_mod :214-218, int32 wrapping
+__global__ void k_complex_mod(const int2 *__restrict__ a, const int2 *__restrict__ b,
+                              int2 *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int2 x = a[i], y = b[i];
+        unsigned re = (unsigned)x.x * (unsigned)y.x - (unsigned)x.y * (unsigned)y.y;
+        unsigned im = (unsigned)x.x * (unsigned)y.y + (unsigned)x.y * (unsigned)y.x;
+        out[i] = make_int2((int)re, (int)im);
+    }
+}
+
+// Java (int)double
+static int java_d2i(double d)
+{
+    if (d != d) return 0;
+    if (d >= 2147483647.0) return INT_MAX;
+    if (d <= -2147483648.0) return INT_MIN;
+    return (int)d;
+}
+
+}  // namespace dsp
+}  // namespace jsdr
+
+using namespace jsdr;
+using namespace jsdr::dsp;
+
+namespace {
+int upload(jsdr_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    JSDR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+int grow(void **p, size_t *cap, size_t bytes)
+{
+    if (*cap >= bytes) return JSDR_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    JSDR_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return JSDR_OK;
+}
+}  // namespace
+
+// =========================================================================== demod
+extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_block_samples, jsdr_demod **out)
+{
+    JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(rate > 0 && nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
+    JSDR_TRY(ctx->bind());
+    jsdr_demod *d = new jsdr_demod();
+    d->ctx = ctx;
+    d->rate = rate;
+    d->nchan = nchan;
+    d->max_block = max_block_samples;
+    d->max_chunks = (max_block_samples + kChunk - 1) / kChunk + 1;
+    d->h_w.assign((size_t)nchan * kTaps, 0.0f);       // taps are zero until weights() runs
+    d->h_phi.assign(nchan, 0.0f);
+    const size_t nc = (size_t)nchan;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_w, sizeof(float) * kTaps * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_phi, sizeof(float) * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_car, sizeof(float) * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_chunk_car, sizeof(float) * nc * d->max_chunks);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_hist[0], sizeof(float2) * kHist * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_hist[1], sizeof(float2) * kHist * nc);
+    if (e != cudaSuccess) {
+        set_error("jsdr_demod_create: %s", cudaGetErrorString(e));
+        jsdr_demod_destroy(d);
+        cudaGetLastError();
+        return JSDR_ENOMEM;
+    }
+    cudaMemsetAsync(d->d_w, 0, sizeof(float) * kTaps * nc, ctx->stream);
+    cudaMemsetAsync(d->d_phi, 0, sizeof(float) * nc, ctx->stream);
+    cudaMemsetAsync(d->d_car, 0, sizeof(float) * nc, ctx->stream);
+    cudaMemsetAsync(d->d_hist[0], 0, sizeof(float2) * kHist * nc, ctx->stream);
+    cudaMemsetAsync(d->d_hist[1], 0, sizeof(float2) * kHist * nc, ctx->stream);
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = d;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_demod_destroy(jsdr_demod *d)
+{
+    if (!d) return JSDR_OK;
+    d->ctx->bind();
+    cudaStreamSynchronize(d->ctx->side);
+    cudaStreamSynchronize(d->ctx->stream);
+    void *ptrs[] = {d->d_w, d->d_phi, d->d_car, d->d_chunk_car, d->d_hist[0], d->d_hist[1], d->d_in, d->d_out};
+    for (void *p : ptrs) cudaFree(p);
+    delete d;
+    return JSDR_OK;
+}
+
+// demod.weights(), demod.java:341-375
+extern "C" int jsdr_demod_weights(jsdr_demod *d, int chan, int flo, int fhi)
+{
+    JSDR_REQUIRE(d && chan >= 0 && chan < d->nchan, JSDR_EINVAL, "bad channel");
+    jsdr_ctx *ctx = d->ctx;
+    JSDR_TRY(ctx->bind());
+    float *w = &d->h_w[(size_t)chan * kTaps];
+    if (flo == INT_MIN) {                               // :343 all-pass; phi and car keep their values
+        for (int i = 0; i < kTaps; i++) w[i] = 0.0f;
+        w[(kTaps - 1) / 2] = 1.0f;
+    } else {
+        float rate = (float)d->rate;
+        float nlo = (float)flo / rate;
+        float nhi = (float)fhi / rate;
+        int ord = kTaps - 1;
+        for (int n = 0; n < kTaps; n++) {
+            if (n == ord / 2) {
+                w[n] = 2.0f * (nhi - nlo);
+            } else {
+                double dn = (double)(n - ord / 2);
+                w[n] = (float)((sin(2 * M_PI * nhi * dn) / (M_PI * dn)) - (sin(2 * M_PI * nlo * dn) / (M_PI * dn)));
+            }
+            w[n] *= (float)(0.54 - 0.46 * cos(2 * M_PI * (double)n / (double)ord));
+        }
+        d->h_phi[chan] = (float)(2 * M_PI * nlo);       // :368
+        const float zero = 0.0f;
+        JSDR_TRY(upload(ctx, d->d_phi + chan, &d->h_phi[chan], sizeof(float)));
+        JSDR_TRY(upload(ctx, d->d_car + chan, &zero, sizeof(float)));   // :369
+    }
+    JSDR_TRY(upload(ctx, d->d_w + (size_t)chan * kTaps, w, sizeof(float) * kTaps));
+    // :372-374 clear the delay line
+    for (int i = 0; i < 2; i++)
+        JSDR_CUDA(cudaMemsetAsync(d->d_hist[i] + (size_t)chan * kHist, 0, sizeof(float2) * kHist, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_demod_get_weights(jsdr_demod *d, int chan, float w[21])
+{
+    JSDR_REQUIRE(d && w && chan >= 0 && chan < d->nchan, JSDR_EINVAL, "bad channel");
+    memcpy(w, &d->h_w[(size_t)chan * kTaps], sizeof(float) * kTaps);
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_demod_set_flags(jsdr_demod *d, int dofir, int dodwn)
+{
+    JSDR_REQUIRE(d, JSDR_EINVAL, "null argument");
+    d->dofir = dofir != 0;
+    d->dodwn = dodwn != 0;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
+                                      float *out, int mem)
+{
+    JSDR_REQUIRE(d && iq && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(S >= 0 && S <= d->max_block, JSDR_EINVAL, "nsamples exceeds max_block_samples");
+    JSDR_REQUIRE(chan_stride == 0 || chan_stride >= S, JSDR_EINVAL, "chan_stride smaller than nsamples");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    if (S == 0) return JSDR_OK;
+    jsdr_ctx *ctx = d->ctx;
+    JSDR_TRY(ctx->bind());
+    const int nchan = d->nchan;
+    if (d->dodwn) {
+        JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        k_car_scout<<<(nchan + 127) / 128, 128, 0, ctx->side>>>(d->d_phi, d->d_car, d->d_chunk_car, nchan, S);
+        JSDR_TRY(launched(ctx, "k_car_scout"));
+        JSDR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+    }
+    const float2 *d_in = reinterpret_cast<const float2 *>(iq);
+    float2 *d_out = reinterpret_cast<float2 *>(out);
+    const size_t out_bytes = sizeof(float2) * (size_t)nchan * S;
+    if (mem == JSDR_MEM_HOST) {
+        const size_t total = (chan_stride == 0) ? (size_t)S : (size_t)chan_stride * (nchan - 1) + S;
+        JSDR_TRY(grow(&d->d_in, &d->in_cap, total * sizeof(float2)));
+        JSDR_TRY(grow(reinterpret_cast<void **>(&d->d_out), &d->out_cap, out_bytes));
+        JSDR_CUDA(cudaMemcpyAsync(d->d_in, iq, total * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        d_in = reinterpret_cast<const float2 *>(d->d_in);
+        d_out = reinterpret_cast<float2 *>(d->d_out);
+    }
+    if (d->dodwn) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    DemodParams p;
+    p.in = d_in;
+    p.chan_stride = chan_stride;
+    p.S = S;
+    p.nchan = nchan;
+    p.w = d->d_w;
+    p.phi = d->d_phi;
+    p.chunk_car = d->d_chunk_car;
+    p.hist_in = d->d_hist[d->hist_cur];
+    p.hist_out = d->d_hist[d->hist_cur ^ 1];
+    p.out = d_out;
+    p.dofir = d->dofir;
+    p.dodwn = d->dodwn;
+    dim3 grid((S + kTile - 1) / kTile, nchan);
+    k_demod<<<grid, kThreads, 0, ctx->stream>>>(p);
+    JSDR_TRY(launched(ctx, "k_demod"));
+    if (d->dofir) {   // the delay line only moves when filter() runs (:415-419)
+        k_demod_tail<<<nchan, 32, 0, ctx->stream>>>(p);
+        JSDR_TRY(launched(ctx, "k_demod_tail"));
+        d->hist_cur ^= 1;
+    }
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMemcpyAsync(out, d->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return JSDR_OK;
+}
+
+// =========================================================================== fir.java
+// fir.weights(), fir.java:169-195 (host, one-off)
+extern "C" int jsdr_fir_design(int f1, int f2, float rate, double w[21])
+{
+    JSDR_REQUIRE(w && rate > 0, JSDR_EINVAL, "bad argument");
+    if (f1 == INT_MIN && f2 == INT_MIN) {
+        for (int i = 0; i < kTaps; i++) w[i] = 0;
+        w[(kTaps - 1) / 2] = 1;
+        return JSDR_OK;
+    }
+    double df1 = (double)f1 / rate;
+    double df2 = (double)f2 / rate;
+    int ord = kTaps - 1;
+    for (int n = 0; n < kTaps; n++) {
+        if (n == ord / 2) {
+            w[n] = 2 * (df2 - df1);
+        } else {
+            int dn = n - ord / 2;
+            w[n] = (sin(2 * M_PI * df2 * dn) / (M_PI * dn)) - (sin(2 * M_PI * df1 * dn) / (M_PI * dn));
+        }
+        w[n] = w[n] * (0.54 - 0.46 * cos(2 * M_PI * n / ord));
+    }
+    return JSDR_OK;
+}
+
+// one period of complex_gen, fir.java:221-228 (the counter wraps at (int)rate)
+extern "C" int jsdr_fir_nco_table(int freq, float rate, int32_t *sig)
+{
+    JSDR_REQUIRE(sig && rate >= 1.0f, JSDR_EINVAL, "bad argument");
+    const int period = (int)rate;
+    for (int n = 0; n < period; n++) {
+        double w = (((2 * M_PI) * freq) * n) / rate;
+        sig[2 * n] = java_d2i(cos(w) * 4096);
+        sig[2 * n + 1] = java_d2i(sin(w) * 4096);
+    }
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fir_create(jsdr_ctx *ctx, int nchan, int max_block_samples, jsdr_fir **out)
+{
+    JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
+    JSDR_TRY(ctx->bind());
+    jsdr_fir *f = new jsdr_fir();
+    f->ctx = ctx;
+    f->nchan = nchan;
+    f->max_block = max_block_samples;
+    const size_t nc = (size_t)nchan;
+    cudaError_t e = cudaMalloc(&f->d_w, sizeof(double) * kTaps * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_hist[0], sizeof(int32_t) * kHist * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_hist[1], sizeof(int32_t) * kHist * nc);
+    if (e != cudaSuccess) {
+        set_error("jsdr_fir_create: %s", cudaGetErrorString(e));
+        jsdr_fir_destroy(f);
+        cudaGetLastError();
+        return JSDR_ENOMEM;
+    }
+    cudaMemsetAsync(f->d_w, 0, sizeof(double) * kTaps * nc, ctx->stream);
+    cudaMemsetAsync(f->d_hist[0], 0, sizeof(int32_t) * kHist * nc, ctx->stream);
+    cudaMemsetAsync(f->d_hist[1], 0, sizeof(int32_t) * kHist * nc, ctx->stream);
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = f;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fir_destroy(jsdr_fir *f)
+{
+    if (!f) return JSDR_OK;
+    f->ctx->bind();
+    cudaStreamSynchronize(f->ctx->stream);
+    void *ptrs[] = {f->d_w, f->d_hist[0], f->d_hist[1], f->d_in, f->d_out};
+    for (void *p : ptrs) cudaFree(p);
+    delete f;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fir_set_weights(jsdr_fir *f, int chan, const double w[21])
+{
+    JSDR_REQUIRE(f && w && chan >= 0 && chan < f->nchan, JSDR_EINVAL, "bad channel");
+    jsdr_ctx *ctx = f->ctx;
+    JSDR_TRY(ctx->bind());
+    JSDR_TRY(upload(ctx, f->d_w + (size_t)chan * kTaps, w, sizeof(double) * kTaps));
+    for (int i = 0; i < 2; i++)                          // :192-193 clear previous samples
+        JSDR_CUDA(cudaMemsetAsync(f->d_hist[i] + (size_t)chan * kHist, 0, sizeof(int32_t) * kHist, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fir_filter_i32(jsdr_fir *f, const int32_t *in, int S, int64_t chan_stride,
+                                   int32_t *out, int mem)
+{
+    JSDR_REQUIRE(f && in && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(S >= 0 && S <= f->max_block, JSDR_EINVAL, "nsamples exceeds max_block_samples");
+    JSDR_REQUIRE(chan_stride == 0 || chan_stride >= S, JSDR_EINVAL, "chan_stride smaller than nsamples");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    if (S == 0) return JSDR_OK;
+    jsdr_ctx *ctx = f->ctx;
+    JSDR_TRY(ctx->bind());
+    const int nchan = f->nchan;
+    const int32_t *d_in = in;
+    int32_t *d_out = out;
+    const size_t out_bytes = sizeof(int32_t) * (size_t)nchan * S;
+    if (mem == JSDR_MEM_HOST) {
+        const size_t total = (chan_stride == 0) ? (size_t)S : (size_t)chan_stride * (nchan - 1) + S;
+        JSDR_TRY(grow(reinterpret_cast<void **>(&f->d_in), &f->in_cap, total * sizeof(int32_t)));
+        JSDR_TRY(grow(reinterpret_cast<void **>(&f->d_out), &f->out_cap, out_bytes));
+        JSDR_CUDA(cudaMemcpyAsync(f->d_in, in, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_in = f->d_in;
+        d_out = f->d_out;
+    }
+    FirParams p;
+    p.in = d_in;
+    p.chan_stride = chan_stride;
+    p.S = S;
+    p.w = f->d_w;
+    p.hist_in = f->d_hist[f->hist_cur];
+    p.hist_out = f->d_hist[f->hist_cur ^ 1];
+    p.out = d_out;
+    dim3 grid((S + kThreads - 1) / kThreads, nchan);
+    k_fir_i32<<<grid, kThreads, 0, ctx->stream>>>(p);
+    JSDR_TRY(launched(ctx, "k_fir_i32"));
+    k_fir_tail<<<nchan, 32, 0, ctx->stream>>>(p);
+    JSDR_TRY(launched(ctx, "k_fir_tail"));
+    f->hist_cur ^= 1;
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMemcpyAsync(out, f->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const int32_t *b, int32_t *out,
+                                        int64_t npairs, int mem)
+{
+    JSDR_REQUIRE(ctx && a && b && out && npairs >= 0, JSDR_EINVAL, "bad argument");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    if (npairs == 0) return JSDR_OK;
+    JSDR_TRY(ctx->bind());
+    const size_t bytes = sizeof(int2) * (size_t)npairs;
+    const int2 *da = reinterpret_cast<const int2 *>(a), *db = reinterpret_cast<const int2 *>(b);
+    int2 *dout = reinterpret_cast<int2 *>(out);
+    void *tmp = nullptr;
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMalloc(&tmp, 3 * bytes));
+        int2 *t = static_cast<int2 *>(tmp);
+        JSDR_CUDA(cudaMemcpyAsync(t, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        JSDR_CUDA(cudaMemcpyAsync(t + npairs, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        da = t;
+        db = t + npairs;
+        dout = t + 2 * npairs;
+    }
+    long long blocks = (npairs + 255) / 256;
+    int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    k_complex_mod<<<grid, 256, 0, ctx->stream>>>(da, db, dout, npairs);
+    JSDR_TRY(launched(ctx, "k_complex_mod"));
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    return JSDR_OK;
+}

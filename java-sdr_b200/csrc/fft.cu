@@ -1,0 +1,183 @@
+// fft.cu — host side of the fft.java replacement (jsdr_fft_* in jsdrcuda.h).
+#include <math.h>
+
+#include <vector>
+
+#include "fft_kernels.cuh"
+#include "fft_plans.h"
+#include "handles.h"
+
+namespace jsdr {
+namespace fft {
+
+#define DECL(N, T, G, R0, R1, R2, R3)                                                         \
+    int launch_n##N(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st); \
+    size_t smem_n##N();
+JSDR_FFT_PLANS(DECL)
+#undef DECL
+
+typedef int (*launch_fn)(jsdr_ctx *, const Args &, int, int, cudaStream_t);
+struct PlanEntry { int n; launch_fn fn; };
+static const PlanEntry kPlans[] = {
+#define ROW(N, T, G, R0, R1, R2, R3) {N, launch_n##N},
+    JSDR_FFT_PLANS(ROW)
+#undef ROW
+};
+
+static const PlanEntry *find_plan(int n)
+{
+    for (const PlanEntry &p : kPlans)
+        if (p.n == n) return &p;
+    return nullptr;
+}
+
+int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, int32_t *d_peak,
+           int out_mode, int ic, int qc, cudaStream_t st)
+{
+    Args a;
+    a.in = d_in;
+    a.out = d_out;
+    a.peak_bin = d_peak;
+    a.tw = f->d_tw;
+    a.nblocks = batch;
+    a.rate = f->rate;
+    // fft.java:199-200  cf = 2f/(float)N; cf = cf*cf  (float arithmetic)
+    float cf = 2.0f / (float)f->n;
+    cf = cf * cf;
+    if (in_fmt == IN_S16) {
+        // JavaAudio.java:283 divides each sample by 32767f before the transform;
+        // the transform is linear, so the scale moves into cf.
+        cf = (float)((double)cf / (32767.0 * 32767.0));
+    }
+    a.cf = cf;
+    a.ic = ic;
+    a.qc = qc;
+    return reinterpret_cast<launch_fn>(f->launch)(f->ctx, a, in_fmt, out_mode, st);
+}
+
+}  // namespace fft
+}  // namespace jsdr
+
+using namespace jsdr;
+
+extern "C" int jsdr_fft_supported(int n) { return fft::find_plan(n) != nullptr; }
+
+extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, jsdr_fft **out)
+{
+    JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(max_batch > 0 && rate > 0, JSDR_EINVAL, "max_batch and rate must be positive");
+    const fft::PlanEntry *p = fft::find_plan(n);
+    if (!p) {
+        set_error("jsdr_fft_create: no FFT plan for n=%d", n);
+        return JSDR_EUNSUPPORTED;
+    }
+    JSDR_TRY(ctx->bind());
+    jsdr_fft *f = new jsdr_fft();
+    f->ctx = ctx;
+    f->n = n;
+    f->rate = rate;
+    f->max_batch = max_batch;
+    f->launch = reinterpret_cast<void *>(p->fn);
+    // twiddle table exp(-2*pi*i*t/n), computed in double, rounded once
+    std::vector<float2> tw(n);
+    for (int t = 0; t < n; t++) {
+        double ang = 2.0 * M_PI * (double)t / (double)n;
+        tw[t] = make_float2((float)cos(ang), (float)-sin(ang));
+    }
+    cudaError_t e = cudaMalloc(&f->d_tw, sizeof(float2) * n);
+    if (e != cudaSuccess) {
+        delete f;
+        set_error("cudaMalloc twiddles: %s", cudaGetErrorString(e));
+        return JSDR_ENOMEM;
+    }
+    e = cudaMemcpyAsync(f->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(f->d_tw);
+        delete f;
+        set_error("twiddle upload: %s", cudaGetErrorString(e));
+        return JSDR_ECUDA;
+    }
+    *out = f;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_fft_destroy(jsdr_fft *f)
+{
+    if (!f) return JSDR_OK;
+    f->ctx->bind();
+    cudaFree(f->d_tw);
+    cudaFree(f->d_in);
+    cudaFree(f->d_out);
+    cudaFree(f->d_peak);
+    delete f;
+    return JSDR_OK;
+}
+
+namespace {
+
+int ensure_staging(jsdr_fft *f, size_t in_bytes, size_t out_bytes)
+{
+    if (f->in_cap < in_bytes) {
+        cudaFree(f->d_in);
+        f->d_in = nullptr;
+        f->in_cap = 0;
+        JSDR_CUDA(cudaMalloc(&f->d_in, in_bytes));
+        f->in_cap = in_bytes;
+    }
+    if (f->out_cap < out_bytes) {
+        cudaFree(f->d_out);
+        f->d_out = nullptr;
+        f->out_cap = 0;
+        JSDR_CUDA(cudaMalloc(&f->d_out, out_bytes));
+        f->out_cap = out_bytes;
+    }
+    if (!f->d_peak) JSDR_CUDA(cudaMalloc(&f->d_peak, sizeof(int32_t) * (size_t)f->max_batch));
+    return JSDR_OK;
+}
+
+// shared body of the three receive flavours
+int fft_run(jsdr_fft *f, const void *in, int in_fmt, int batch, int ic, int qc, float *out,
+            int32_t *peak_bin, int out_mode, int mem)
+{
+    JSDR_REQUIRE(f && in && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(batch >= 0 && batch <= f->max_batch, JSDR_EINVAL, "batch exceeds max_batch");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    if (batch == 0) return JSDR_OK;   // empty input: nothing to publish
+    jsdr_ctx *ctx = f->ctx;
+    JSDR_TRY(ctx->bind());
+    const size_t n = (size_t)f->n;
+    const size_t in_bytes = (size_t)batch * n * (in_fmt == fft::IN_S16 ? 4 : 8);
+    const size_t out_elems = (size_t)batch * (out_mode == fft::OUT_PSD ? n + 2 : 2 * n);
+    if (mem == JSDR_MEM_DEVICE) {
+        return fft::launch(f, in, in_fmt, batch, out, peak_bin, out_mode, ic, qc, ctx->stream);
+    }
+    JSDR_TRY(ensure_staging(f, in_bytes, out_elems * sizeof(float)));
+    JSDR_CUDA(cudaMemcpyAsync(f->d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    JSDR_TRY(fft::launch(f, f->d_in, in_fmt, batch, f->d_out, f->d_peak, out_mode, ic, qc, ctx->stream));
+    JSDR_CUDA(cudaMemcpyAsync(out, f->d_out, out_elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (peak_bin && out_mode == fft::OUT_PSD)
+        JSDR_CUDA(cudaMemcpyAsync(peak_bin, f->d_peak, sizeof(int32_t) * (size_t)batch,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+}  // namespace
+
+extern "C" int jsdr_fft_receive_f32(jsdr_fft *f, const float *iq, int batch, float *psd,
+                                    int32_t *peak_bin, int mem)
+{
+    return fft_run(f, iq, fft::IN_F32, batch, 0, 0, psd, peak_bin, fft::OUT_PSD, mem);
+}
+
+extern "C" int jsdr_fft_receive_s16(jsdr_fft *f, const int16_t *raw, int batch, int ic, int qc,
+                                    float *psd, int32_t *peak_bin, int mem)
+{
+    return fft_run(f, raw, fft::IN_S16, batch, ic, qc, psd, peak_bin, fft::OUT_PSD, mem);
+}
+
+extern "C" int jsdr_fft_forward_f32(jsdr_fft *f, const float *iq, int batch, float *spec, int mem)
+{
+    return fft_run(f, iq, fft::IN_F32, batch, 0, 0, spec, nullptr, fft::OUT_SPECTRUM, mem);
+}

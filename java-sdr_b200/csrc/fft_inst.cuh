@@ -1,0 +1,45 @@
+// fft_inst.cuh — one translation unit per FFT length includes this with
+// JSDR_FFT_N etc. defined, so the plans compile in parallel.
+#pragma once
+#include "fft_kernels.cuh"
+
+namespace jsdr {
+namespace fft {
+
+template <class P, int IN, int OUT>
+static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
+{
+    static bool attr_done = false;
+    auto kern = fft_kernel<P, IN, OUT>;
+    if (!attr_done) {
+        JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+        attr_done = true;
+    }
+    int grid = (a.nblocks + P::G - 1) / P::G;
+    if (grid <= 0) return JSDR_OK;
+    kern<<<grid, P::T, P::SMEM, st>>>(a);
+    return launched(ctx, "fft_kernel");
+}
+
+template <class P>
+static int launch_plan(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st)
+{
+    if (out_mode == OUT_SPECTRUM) {
+        if (in_fmt != IN_F32) { set_error("spectrum output needs float input"); return JSDR_EINVAL; }
+        return launch_one<P, IN_F32, OUT_SPECTRUM>(ctx, a, st);
+    }
+    if (in_fmt == IN_F32) return launch_one<P, IN_F32, OUT_PSD>(ctx, a, st);
+    return launch_one<P, IN_S16, OUT_PSD>(ctx, a, st);
+}
+
+}  // namespace fft
+}  // namespace jsdr
+
+#define JSDR_FFT_DEFINE(N, T, G, R0, R1, R2, R3)                                               \
+    namespace jsdr { namespace fft {                                                           \
+    int launch_n##N(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st)   \
+    {                                                                                          \
+        return launch_plan<Plan<N, T, G, R0, R1, R2, R3>>(ctx, a, in_fmt, out_mode, st);       \
+    }                                                                                          \
+    size_t smem_n##N() { return Plan<N, T, G, R0, R1, R2, R3>::SMEM; }                         \
+    } }

@@ -1,0 +1,440 @@
+// fft_kernels.cuh — batched complex FFT + power spectrum for sm_100a.
+//
+// Replaces the arithmetic behind fft.receive (reference fft.java:190-228): an
+// unnormalised forward complex DFT (JTransforms FloatFFT_1D.complexForward,
+// fft.java:194-195) followed by psd = 10*log10((re^2+im^2)*(2/N)^2)
+// (fft.java:199-207), the first strict maximum (:208-211) and its frequency in
+// wrapping int32 arithmetic (:214-221).
+//
+// Structure: one CTA transforms G whole blocks in shared memory.
+//   pass 0     reads x[c + m*N/R0] straight from HBM (each warp request is a
+//              contiguous run), does an R0-point DFT in registers and scatters the
+//              R0 results as one contiguous chunk to the digit-reversed row,
+//              so every later pass is in place;
+//   middle     in-place radix-Rp butterflies, twiddle before the butterfly (DIT);
+//   last pass  radix-RL butterfly whose outputs are bins j + q*N/RL, i.e. natural
+//              order with consecutive lanes on consecutive bins: the PSD epilogue
+//              (|X|^2*cf -> dB, arg-max) is fused here and the spectrum is never
+//              written back to shared memory.
+// Rows (one per last-pass input) are padded so that the chunk scatter of pass 0
+// does not bank-conflict.  The index plan is emulated in tools/fft_plan_emulate.py.
+#pragma once
+
+#include <type_traits>
+
+#include "handles.h"
+
+namespace jsdr {
+namespace fft {
+
+// ------------------------------------------------------------------ constants
+__host__ __device__ constexpr double cx_pi() { return 3.14159265358979323846264338327950288; }
+
+__host__ __device__ constexpr double cx_sin_small(double x)
+{   // |x| <= pi/4, Taylor to ~1e-19
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i < 14; i++) {
+        term *= -x2 / (double)((2 * i) * (2 * i + 1));
+        sum += term;
+    }
+    return sum;
+}
+__host__ __device__ constexpr double cx_cos_small(double x)
+{
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i < 14; i++) {
+        term *= -x2 / (double)((2 * i - 1) * (2 * i));
+        sum += term;
+    }
+    return sum;
+}
+// cos / sin of 2*pi*k/r with the octant reduced on the integers
+__host__ __device__ constexpr double cx_cos2pi(int k, int r)
+{
+    k %= r;
+    if (k < 0) k += r;
+    // work in eighths of a turn: a / (8r) turns
+    long a = 8L * k, q = r;            // angle = 2*pi*a/(8q)
+    if (a > 4 * q) a = 8 * q - a;      // cos(2pi - t) = cos t
+    bool neg = false;
+    if (a > 2 * q) { a = 4 * q - a; neg = true; }     // cos(pi - t) = -cos t
+    double v = 0;
+    if (a > q) v = cx_sin_small(2.0 * cx_pi() * (double)(2 * q - a) / (double)(8 * q));  // cos t = sin(pi/2 - t)
+    else v = cx_cos_small(2.0 * cx_pi() * (double)a / (double)(8 * q));
+    return neg ? -v : v;
+}
+__host__ __device__ constexpr double cx_sin2pi(int k, int r)
+{
+    // sin t = cos(t - pi/2) = cos(2*pi*(k/r - 1/4)) = cos(2*pi*(4k - r)/(4r))
+    return cx_cos2pi(4 * k - r, 4 * r);
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// a * exp(-2*pi*i*K/R), K and R compile-time
+template <int K, int R>
+__device__ __forceinline__ float2 cmul_w(float2 a)
+{
+    constexpr int k = ((K % R) + R) % R;
+    if constexpr (k == 0) return a;
+    else if constexpr (4 * k == R) return make_float2(a.y, -a.x);        // * (-i)
+    else if constexpr (2 * k == R) return make_float2(-a.x, -a.y);
+    else if constexpr (4 * k == 3 * R) return make_float2(-a.y, a.x);    // * (+i)
+    else {
+        constexpr float c = (float)cx_cos2pi(k, R);
+        constexpr float s = (float)(-cx_sin2pi(k, R));
+        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+// ------------------------------------------------------------------ register DFTs
+constexpr int pick_factor(int r)
+{
+    if (r % 4 == 0) return 4;
+    if (r % 2 == 0) return 2;
+    for (int p = 3; p * p <= r; p += 2)
+        if (r % p == 0) return p;
+    return r;
+}
+constexpr bool is_base(int r) { return r == 1 || r == 2 || r == 4 || (r % 2 == 1 && pick_factor(r) == r); }
+
+template <int R, bool BASE = is_base(R)>
+struct Dft;
+
+template <>
+struct Dft<1, true> {
+    static __device__ __forceinline__ void run(float2 *) {}
+};
+
+template <>
+struct Dft<2, true> {
+    static __device__ __forceinline__ void run(float2 *v)
+    {
+        float2 a = v[0], b = v[1];
+        v[0] = make_float2(a.x + b.x, a.y + b.y);
+        v[1] = make_float2(a.x - b.x, a.y - b.y);
+    }
+};
+
+template <>
+struct Dft<4, true> {
+    static __device__ __forceinline__ void run(float2 *v)
+    {
+        float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
+        float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+        float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
+        float2 a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+        v[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+        v[1] = make_float2(a1.x + a3.y, a1.y - a3.x);   // a1 - i*a3
+        v[2] = make_float2(a0.x - a2.x, a0.y - a2.y);
+        v[3] = make_float2(a1.x - a3.y, a1.y + a3.x);   // a1 + i*a3
+    }
+};
+
+// odd prime P: pair x[n] with x[P-n]
+template <int P>
+struct Dft<P, true> {
+    static __device__ __forceinline__ void run(float2 *v)
+    {
+        constexpr int H = (P - 1) / 2;
+        float2 s[H + 1], d[H + 1];
+#pragma unroll
+        for (int n = 1; n <= H; n++) {
+            s[n] = make_float2(v[n].x + v[P - n].x, v[n].y + v[P - n].y);
+            d[n] = make_float2(v[n].x - v[P - n].x, v[n].y - v[P - n].y);
+        }
+        float2 x0 = v[0];
+        float2 acc = x0;
+#pragma unroll
+        for (int n = 1; n <= H; n++) { acc.x += s[n].x; acc.y += s[n].y; }
+        v[0] = acc;
+        static_for<1, H + 1>([&](auto kk) {
+            constexpr int k = decltype(kk)::value;
+            float2 re = x0, im = make_float2(0.f, 0.f);
+            static_for<1, H + 1>([&](auto nn) {
+                constexpr int n = decltype(nn)::value;
+                constexpr float c = (float)cx_cos2pi(n * k, P);
+                constexpr float sn = (float)cx_sin2pi(n * k, P);
+                re.x = fmaf(s[n].x, c, re.x);
+                re.y = fmaf(s[n].y, c, re.y);
+                im.x = fmaf(d[n].x, sn, im.x);
+                im.y = fmaf(d[n].y, sn, im.y);
+            });
+            // X[k] = re - i*im ; X[P-k] = re + i*im
+            v[k] = make_float2(re.x + im.y, re.y - im.x);
+            v[P - k] = make_float2(re.x - im.y, re.y + im.x);
+        });
+    }
+};
+
+// composite R = A*B: n = B*n1 + n2, k = k1 + A*k2
+template <int R>
+struct Dft<R, false> {
+    static constexpr int A = pick_factor(R);
+    static constexpr int B = R / A;
+    static __device__ __forceinline__ void run(float2 *v)
+    {
+        float2 t[R];
+        static_for<0, B>([&](auto nn2) {
+            constexpr int n2 = decltype(nn2)::value;
+            float2 a[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; n1++) a[n1] = v[B * n1 + n2];
+            Dft<A>::run(a);
+            static_for<0, A>([&](auto kk1) {
+                constexpr int k1 = decltype(kk1)::value;
+                t[k1 * B + n2] = cmul_w<n2 * k1, R>(a[k1]);
+            });
+        });
+#pragma unroll
+        for (int k1 = 0; k1 < A; k1++) {
+            float2 b[B];
+#pragma unroll
+            for (int n2 = 0; n2 < B; n2++) b[n2] = t[k1 * B + n2];
+            Dft<B>::run(b);
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) v[k1 + A * k2] = b[k2];
+        }
+    }
+};
+
+// v[r] *= w1^r for r = 1..R-1, powers by a balanced product tree (depth log2 R)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 *v, float2 w1)
+{
+    float2 w[R];
+    w[0] = make_float2(1.f, 0.f);
+    if (R > 1) w[1] = w1;
+#pragma unroll
+    for (int r = 2; r < R; r++) w[r] = cmul(w[r / 2], w[r - r / 2]);
+#pragma unroll
+    for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
+}
+
+// ------------------------------------------------------------------ plan
+template <int N_, int T_, int G_, int R0_, int R1_, int R2_ = 1, int R3_ = 1>
+struct Plan {
+    static constexpr int N = N_, T = T_, G = G_;
+    static constexpr int R0 = R0_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int K = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : 2;
+    static constexpr int RL = (K == 4) ? R3_ : (K == 3) ? R2_ : R1_;
+    static constexpr int ML = N_ / RL;                       // row length
+    static constexpr int PAD = (ML % 4 == 0) ? 2 : 4;        // keeps (ML+PAD)/2 odd
+    static constexpr int PITCH = ML + PAD;
+    static constexpr int FFT_ELEMS = RL * PITCH;             // float2 per block in smem
+    static constexpr size_t SMEM = (size_t)G_ * FFT_ELEMS * sizeof(float2);
+    static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+    static_assert(R0_ % 2 == 0 && ML % 2 == 0, "chunk scatter uses 16-byte stores");
+    static_assert(G_ == 1 || T_ == G_ * ML, "multi-block CTAs need one last-pass round");
+};
+
+struct Args {
+    const void *in;       // float2[nblocks][N] or int16x2[nblocks][N]
+    float *out;           // float[nblocks][N+2] (PSD) or float2[nblocks][N] (spectrum)
+    int32_t *peak_bin;    // nullable
+    const float2 *tw;     // exp(-2*pi*i*t/N), t in [0,N)
+    int nblocks;
+    int rate;
+    float cf;             // (2/N)^2, times 1/32767^2 for s16 input
+    int ic, qc;           // I/Q DC correction added with 16-bit wrap (s16 input)
+};
+
+__device__ __forceinline__ unsigned ordered_key(float v)
+{   // monotone float -> uint; 0 means "not a candidate" (NaN, -inf, <= -FLT_MAX)
+    if (!(v > -3.4028234663852886e38f)) return 0u;
+    unsigned u = __float_as_uint(v + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <class P, int IN>
+__device__ __forceinline__ float2 load_sample(const Args &a, long blk, int n)
+{
+    if constexpr (IN == IN_F32) {
+        return ldg_stream_f2(reinterpret_cast<const float2 *>(a.in) + blk * P::N + n);
+    } else {
+        uint32_t w = ldg_stream_u32(reinterpret_cast<const uint32_t *>(a.in) + blk * P::N + n);
+        // JavaAudio.java:281-288: s += (short)ic with 16-bit wrap, then (float)s.
+        // The 1/32767 scale is folded into cf (the transform is linear).
+        short si = (short)((int)(w & 0xffffu) + a.ic);
+        short sq = (short)((int)(w >> 16) + a.qc);
+        return make_float2((float)si, (float)sq);
+    }
+}
+
+template <int R, int M>
+__device__ __forceinline__ void load_strided(float2 *v, const float2 *p)
+{
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = p[r * M];
+}
+
+// middle pass p: sub-transform length L = M*R, butterfly stride M
+template <class P, int R, int M>
+__device__ __forceinline__ void middle_pass(float2 *sm, const float2 *__restrict__ tw, int tid)
+{
+    constexpr int L = M * R;
+    constexpr int NB = P::N / R;
+    for (int U = tid; U < P::G * NB; U += P::T) {
+        int g = U / NB, u = U - g * NB;
+        int j = u % M, blk = u / M;
+        int lin = blk * L + j;
+        float2 *p = sm + g * P::FFT_ELEMS + lin + (lin / P::ML) * P::PAD;
+        float2 v[R];
+        load_strided<R, M>(v, p);
+        float2 w1 = __ldg(tw + j * (P::N / L));
+        twiddle_powers<R>(v, w1);
+        Dft<R>::run(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) p[r * M] = v[r];
+    }
+}
+
+template <class P, int IN, int OUT>
+__global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ unsigned s_max[P::G];
+    __shared__ int s_idx[P::G];
+
+    const int tid = threadIdx.x;
+    const long blk0 = (long)blockIdx.x * P::G;
+    constexpr int N = P::N;
+
+    if (OUT == OUT_PSD && tid < P::G) {
+        s_max[tid] = 0u;
+        s_idx[tid] = 0x7fffffff;
+    }
+
+    // ---------------- pass 0: HBM -> registers -> DFT_R0 -> digit-reversed chunk
+    {
+        constexpr int R0 = P::R0;
+        constexpr int NB0 = N / R0;
+        for (int U = tid; U < P::G * NB0; U += P::T) {
+            int g = U / NB0, c = U - g * NB0;
+            long blk = blk0 + g;
+            if (blk >= a.nblocks) continue;
+            float2 v[R0];
+#pragma unroll
+            for (int m = 0; m < R0; m++) v[m] = load_sample<P, IN>(a, blk, c + m * NB0);
+            Dft<R0>::run(v);
+            int pos;
+            if constexpr (P::K == 2) {
+                pos = c * P::PITCH;
+            } else if constexpr (P::K == 3) {
+                int r2 = c % P::R2, r1 = c / P::R2;
+                pos = r2 * P::PITCH + r1 * R0;
+            } else {
+                int r3 = c % P::R3, t = c / P::R3;
+                int r2 = t % P::R2, r1 = t / P::R2;
+                pos = r3 * P::PITCH + r2 * (R0 * P::R1) + r1 * R0;
+            }
+            float4 *dst = reinterpret_cast<float4 *>(sm + g * P::FFT_ELEMS + pos);
+#pragma unroll
+            for (int m = 0; m < R0 / 2; m++)
+                dst[m] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- middle passes (in place)
+    if constexpr (P::K >= 3) {
+        middle_pass<P, P::R1, P::R0>(sm, a.tw, tid);
+        __syncthreads();
+    }
+    if constexpr (P::K >= 4) {
+        middle_pass<P, P::R2, P::R0 * P::R1>(sm, a.tw, tid);
+        __syncthreads();
+    }
+
+    // ---------------- last pass + epilogue
+    {
+        constexpr int RL = P::RL, ML = P::ML;
+        unsigned best_key = 0u;
+        int best_idx = 0x7fffffff;
+        int my_g = 0;
+        for (int U = tid; U < P::G * ML; U += P::T) {
+            int g = U / ML, j = U - g * ML;
+            long blk = blk0 + g;
+            my_g = g;
+            if (blk >= a.nblocks) continue;
+            float2 v[RL];
+            const float2 *p = sm + g * P::FFT_ELEMS + j;
+#pragma unroll
+            for (int r = 0; r < RL; r++) v[r] = p[r * P::PITCH];
+            float2 w1 = __ldg(a.tw + j);
+            twiddle_powers<RL>(v, w1);
+            Dft<RL>::run(v);
+            if constexpr (OUT == OUT_SPECTRUM) {
+                float2 *spec = reinterpret_cast<float2 *>(a.out) + blk * N;
+#pragma unroll
+                for (int q = 0; q < RL; q++) stg_stream_f2(spec + j + q * ML, v[q]);
+            } else {
+                float *psd = a.out + blk * (long)(N + 2);
+#pragma unroll
+                for (int q = 0; q < RL; q++) {
+                    // fft.java:207 in float: (re*re + im*im) * cf, each step rounded
+                    float pw = __fmul_rn(__fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y)), a.cf);
+                    float db = 10.0f * log10f(pw);
+                    int k = j + q * ML;
+                    stg_stream_f32(psd + k, db);
+                    unsigned key = ordered_key(db);
+                    if (key > best_key || (key == best_key && key != 0u && k < best_idx)) {
+                        best_key = key;
+                        best_idx = k;
+                    }
+                }
+            }
+        }
+        if constexpr (OUT == OUT_PSD) {
+            // first strict maximum (fft.java:208-211): max value, lowest bin among equals
+            constexpr bool WARP_UNIFORM = (P::G == 1) || (ML % 32 == 0);
+            unsigned k1 = best_key;
+            if constexpr (WARP_UNIFORM) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) k1 = max(k1, __shfl_xor_sync(0xffffffffu, k1, o));
+                if ((tid & 31) == 0 && k1 != 0u) atomicMax(&s_max[my_g], k1);
+            } else {
+                if (k1 != 0u) atomicMax(&s_max[my_g], k1);
+            }
+            __syncthreads();
+            unsigned gmax = s_max[my_g];
+            if (best_key != 0u && best_key == gmax) atomicMin(&s_idx[my_g], best_idx);
+            __syncthreads();
+            if (tid < P::G && blk0 + tid < a.nblocks) {
+                long blk = blk0 + tid;
+                float *psd = a.out + blk * (long)(N + 2);
+                unsigned key = s_max[tid];
+                int bin = (key != 0u) ? s_idx[tid] : -1;
+                float m = -3.4028234663852886e38f;
+                if (key != 0u) {
+                    unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+                    m = __uint_as_float(u);
+                }
+                // fft.java:214-221 with p = 2*bin, dat.length = 2N, int32 wrap, trunc division
+                int p = (bin < 0) ? -1 : 2 * bin;
+                const int datlen = 2 * N;
+                if (p >= datlen / 2) p -= datlen;
+                p = (int)((unsigned)p * (unsigned)a.rate) / datlen;
+                psd[N] = (float)p;
+                psd[N + 1] = m;
+                if (a.peak_bin) a.peak_bin[blk] = bin;
+            }
+        }
+    }
+}
+
+}  // namespace fft
+}  // namespace jsdr

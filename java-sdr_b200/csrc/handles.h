@@ -1,0 +1,114 @@
+// handles.h — the opaque handle types behind include/jsdrcuda.h.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct jsdr_fft {
+    jsdr_ctx *ctx = nullptr;
+    int n = 0, rate = 0, max_batch = 0;
+    void *launch = nullptr;          // jsdr::fft::launch_fn of the plan
+    float2 *d_tw = nullptr;          // exp(-2*pi*i*t/n)
+    // staging for host-pointer calls (allocated on first use)
+    void *d_in = nullptr;
+    float *d_out = nullptr;
+    int32_t *d_peak = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+};
+
+namespace jsdr {
+namespace bpsk {
+
+// per-channel state of the bit-timing state machine (FUNcubeBPSKDemod.java:497-502)
+struct TimingState {
+    double dmEnergy[8];
+    double dmEnergyOut;
+    double lastI, lastQ;
+    int bitPos, peakPos, newPeak, pad;
+    long long cntBit;
+};
+
+constexpr int kChunk = 32;           // samples between tuner phase checkpoints
+constexpr int kMaxDsTaps = 128;
+constexpr int kDmTaps = 65;          // MATCHED_FILTER_SIZE
+
+}  // namespace bpsk
+}  // namespace jsdr
+
+struct jsdr_bpsk {
+    jsdr_ctx *ctx = nullptr;
+    int rate = 0, D = 0, nchan = 0, max_block = 0, stages = 3;
+    int ntaps = 27;
+    int max_ds = 0, max_chunks = 0, max_bits = 0;
+    std::vector<double> h_tuning;
+
+    double *d_taps = nullptr;        // [kMaxDsTaps] decimator low-pass
+    double *d_dmtaps = nullptr;      // [65] matched filter
+    double *d_cossin = nullptr;      // cosTab[256] then sinTab[256]
+
+    double *d_tu_inc = nullptr;      // [nchan] tuPhaseInc
+    double *d_tu_phase = nullptr;    // [nchan] tuPhase (carried)
+    double *d_chunk_phase = nullptr; // [max_chunks][nchan] phase before each chunk
+    double2 *d_ds_hist[2] = {nullptr, nullptr};   // [nchan][kMaxDsTaps] last ntaps-1 mixed samples
+    int ds_hist_cur = 0;
+    int ds_cnt = 0;                  // dsCnt carry (identical for all channels)
+    int64_t cnt_raw = 0, cnt_ds = 0; // cntRaw / cntDS (identical for all channels)
+    double2 *d_ds_out = nullptr;     // [nchan][max_ds]
+    int last_nds = 0;
+
+    double *d_vco_state = nullptr;   // [2] vcoPhase, dmBitPhase (channel independent)
+    uint8_t *d_vco_ix = nullptr;     // [max_ds] table index per 9600 S/s sample
+    uint8_t *d_bit_roll = nullptr;   // [max_ds] 1 where dmBitPhase rolled over
+    double2 *d_dm_hist[2] = {nullptr, nullptr};   // [nchan][64] last 64 VCO-mixed samples
+    int dm_hist_cur = 0;
+    double2 *d_dm_out = nullptr;     // [nchan][max_ds]
+
+    jsdr::bpsk::TimingState *d_ts = nullptr;   // [nchan]
+    int8_t *d_bits = nullptr;        // [nchan][max_bits]
+    long long *d_bit_at = nullptr;   // [nchan][max_bits]
+    int32_t *d_nbits = nullptr;      // [nchan]
+
+    void *d_in = nullptr;            // staging for host-pointer calls
+    size_t in_cap = 0;
+};
+
+struct jsdr_demod {
+    jsdr_ctx *ctx = nullptr;
+    int rate = 0, nchan = 0, max_block = 0, max_chunks = 0;
+    int dofir = 1, dodwn = 1;
+    std::vector<float> h_w;          // [nchan][21]
+    std::vector<float> h_phi;        // [nchan]
+    float *d_w = nullptr;            // [nchan][21]
+    float *d_phi = nullptr;          // [nchan]
+    float *d_car = nullptr;          // [nchan] carried phase
+    float *d_chunk_car = nullptr;    // [max_chunks][nchan]
+    float2 *d_hist[2] = {nullptr, nullptr};   // [nchan][20] last 20 input samples
+    int hist_cur = 0;
+    void *d_in = nullptr;
+    float *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+};
+
+struct jsdr_fir {
+    jsdr_ctx *ctx = nullptr;
+    int nchan = 0, max_block = 0;
+    double *d_w = nullptr;           // [nchan][21]
+    int32_t *d_hist[2] = {nullptr, nullptr};  // [nchan][20]
+    int hist_cur = 0;
+    int32_t *d_in = nullptr, *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+};
+
+namespace jsdr {
+namespace fft {
+enum { IN_F32 = 0, IN_S16 = 1 };
+enum { OUT_PSD = 0, OUT_SPECTRUM = 1 };
+// enqueue one batched transform on `st` (all pointers are device memory)
+int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, int32_t *d_peak,
+           int out_mode, int ic, int qc, cudaStream_t st);
+}  // namespace fft
+}  // namespace jsdr

@@ -1,0 +1,61 @@
+"""CPU tests of the boundary: libjsdrcuda.so loads, exports every symbol
+include/jsdrcuda.h declares, and fails loudly without a device (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import jsdrcuda
+
+
+def _declared():
+    src = open(jsdrcuda.HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jsdr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = jsdrcuda.lib()
+    names = _declared()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in jsdrcuda.h but not exported"
+    assert names == jsdrcuda.EXPORTS, "python binding and header disagree on the symbol list"
+    assert lib.jsdr_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device context creation must fail, not fall back."""
+    lib = jsdrcuda.lib()
+    n = ctypes.c_int(-1)
+    rc = lib.jsdr_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(jsdrcuda.JsdrError):
+        jsdrcuda.Context(0)
+
+
+def test_host_side_helpers_need_no_device():
+    import numpy as np
+    assert jsdrcuda.fft_supported(4096) and jsdrcuda.fft_supported(19200) and not jsdrcuda.fft_supported(4097)
+    w = np.empty(21)
+    assert jsdrcuda.lib().jsdr_fir_design(500, 1500, ctypes.c_float(44100.0), w.ctypes.data_as(ctypes.c_void_p)) == 0
+    import oracle as O
+    assert np.array_equal(w, O.Fir(44100.0).weights(500, 1500))
+    t = np.empty((44100, 2), dtype=np.int32)
+    assert jsdrcuda.lib().jsdr_fir_nco_table(1000, ctypes.c_float(44100.0), t.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(t[:64], O.Fir(44100.0).complex_gen(1000, 0, 64))
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "java-sdr_b200")
+    for dp, _, files in os.walk(pkg):
+        if "build" in dp:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py", ".java")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "orc_" not in txt and "jsdr_oracle" not in txt and "import oracle" not in txt, f
