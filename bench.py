@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s (complex IQ) through mix + FIR + FFT on B200.
+
+One step = one pass of the hot path over one batch of synthetic s16 IQ
+(BASELINE config 4/5): for every channel, every block goes to the fft handler
+(FFT + PSD, fft.java:190-228) and the whole stream goes through the FUNcube
+tuner + decimating FIR (FUNcubeBPSKDemod.java:382-397, 467-492), via the C ABI's
+jsdr_pump_receive_s16 — the batched form of JavaAudio.run's fan-out.
+
+  value   whole-job Msamples/s with the batch resident in HBM
+  e2e     the same call with HOST (pinned) buffers: H2D of the raw IQ and D2H of
+          the published PSD + a decimated-output read inside the timed region
+  roofline  the dominant kernel (FFT+PSD) timed alone with CUDA events
+  cpu_baseline  the oracle port of the same pipeline on the host cores (rank 0, N=1)
+
+`--impl reference` times the CPU port only (no JVM / JTransforms jar exists in this
+image, so the reference's own Java cannot be run).
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under
+torch.distributed.run, one rank per GPU, no data-path collective (channels shard).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "java-sdr_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+RATE = 192000
+D = RATE // 9600
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--channels", type=int, default=4096, help="independent streams per GPU")
+    ap.add_argument("--fft-n", type=int, default=16384, help="block length (complex samples)")
+    ap.add_argument("--blocks", type=int, default=32, help="blocks per channel per step")
+    ap.add_argument("--taps", type=int, default=64, help="decimator taps (config 4: 64)")
+    ap.add_argument("--e2e-channels", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload_name(a):
+    return (f"config5: {a.channels} ch x {a.blocks} blk x N={a.fft_n} s16 IQ @192kS/s per GPU "
+            f"({a.channels * a.blocks * a.fft_n} samples): FFT+PSD per block + NCO mix + {a.taps}-tap FIR decimate x{D}")
+
+
+def synth_tile(nchan, S, seed):
+    """Synthetic FUNcube-shaped IQ: a BPSK-like carrier near each channel's tuning in noise."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = rng.integers(-6000, 6000, size=(nchan, 2 * S), dtype=np.int16)
+    t = np.arange(S)
+    car = (8000 * np.cos(2 * np.pi * 13200.0 / RATE * t)).astype(np.int16)
+    sar = (8000 * np.sin(2 * np.pi * 13200.0 / RATE * t)).astype(np.int16)
+    out[:, 0::2] += car
+    out[:, 1::2] += sar
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_pipeline(a, seconds, nthreads):
+    """The oracle port of the same pipeline on a bounded sample; returns the cpu_baseline object."""
+    import oracle as O
+    from oracle import siggen
+    taps = siggen.lowpass_taps(a.taps, 4800.0, RATE)
+    nblk = 1
+    probe_ch = max(nthreads, 1) * 2
+    rng = np.random.Generator(np.random.PCG64(7))
+    def run(nch):
+        raw = synth_tile(nch, nblk * a.fft_n, 99)
+        tun = rng.uniform(2000, 90000, nch)
+        t0 = time.perf_counter()
+        _, _, used = O.baseline_pipeline_s16(raw, nch, nblk, a.fft_n, RATE, tun, taps, nthreads)
+        return time.perf_counter() - t0, used
+    dt, used = run(probe_ch)
+    per_ch = dt / probe_ch
+    nch = int(max(probe_ch, min(seconds / max(per_ch, 1e-9), 200000)))
+    nch = (nch // max(nthreads, 1)) * max(nthreads, 1)
+    dt, used = run(nch)
+    v = nch * nblk * a.fft_n / dt / 1e6
+    return {"value": round(v, 3), "unit": "Msamples/s", "cores": used, "kind": "port",
+            "sample": f"{nch} channels x {nblk} block x N={a.fft_n} of the same pipeline "
+                      f"(s16->float, float FFT with per-block plan + PSD, tuner + {a.taps}-tap decimator), "
+                      f"{dt:.1f} s on {used} threads; C port of the Java arithmetic (no JVM in this image)"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(a.steps + a.warmup, 1)))
+    for _ in range(a.warmup):
+        cpu_pipeline(a, min(per_step, 2.0), nthreads)
+    vals, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        last = cpu_pipeline(a, per_step, nthreads)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    last["value"] = round(v, 3)
+    line = {"impl": "reference", "metric": "Msamples/s (complex IQ) through mix+FIR+FFT", "value": round(v, 3),
+            "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(1000 * wall / max(a.steps, 1), 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU port of the reference on the host cores, bounded sample per step"},
+            "cpu_baseline": last,
+            "e2e": {"value": round(v, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import jsdrcuda as J
+
+    ctx = J.Context(local)
+    adsc = J.AudioDescriptor(RATE)
+    n, nblk, nchan = a.fft_n, a.blocks, a.channels
+    S = n * nblk
+    batch = nchan * nblk
+    samples = nchan * S
+
+    rng = np.random.Generator(np.random.PCG64(7 + rank))
+    tuning = rng.uniform(2000, 90000, nchan)
+    taps = J.design_lowpass(a.taps, 4800.0, RATE)
+
+    f = J.fft(ctx, None, adsc, max_batch=batch, n=n)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S, stages=1)
+    bank.set_ds_filter(taps)
+
+    d_raw = ctx.dev_alloc(samples * 4)
+    d_psd = ctx.dev_alloc(batch * (n + 2) * 4)
+    d_peak = ctx.dev_alloc(batch * 4)
+    # fill the resident batch from a 64-channel synthetic tile
+    tile_ch = min(64, nchan)
+    tile = synth_tile(tile_ch, S, 1000 + rank)
+    for c0 in range(0, nchan, tile_ch):
+        k = min(tile_ch, nchan - c0)
+        d_raw.upload(tile[:k], offset=c0 * S * 4)
+
+    def step():
+        J.pump_receive_s16(f, bank, d_raw, nblk, d_psd, d_peak, mem=J.MEM_DEVICE)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        step()
+    ms = ctx.timer_stop_ms()
+    launches = ctx.launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel alone (FFT+PSD), CUDA events on the launching stream
+    for _ in range(2):
+        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
+    fft_ms = ctx.timer_stop_ms() / a.steps
+    # ---- second kernel alone (tuner + decimator incl. its phase scout)
+    for _ in range(2):
+        bank.receive_dev(d_raw, S, S, s16=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        bank.receive_dev(d_raw, S, S, s16=True)
+    mix_ms = ctx.timer_stop_ms() / a.steps
+
+    # ---- end to end through the C ABI with host (pinned) buffers
+    e_ch = min(a.e2e_channels, nchan)
+    e_batch = e_ch * nblk
+    bank_e = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning[:e_ch], max_block=S, stages=1)
+    bank_e.set_ds_filter(taps)
+    f_e = J.fft(ctx, None, adsc, max_batch=e_batch, n=n)
+    h_raw = ctx.host_alloc((e_ch, 2 * S), np.int16)
+    h_psd = ctx.host_alloc((e_batch, n + 2), np.float32)
+    h_pk = ctx.host_alloc((e_batch,), np.int32)
+    h_ds = ctx.host_alloc((e_ch, S // D, 2), np.float64)
+    h_raw[:] = tile[np.arange(e_ch) % tile_ch]
+    def e2e_step():
+        J.pump_receive_s16(f_e, bank_e, h_raw, nblk, h_psd, h_pk, mem=J.MEM_HOST)   # H2D raw, D2H PSD inside
+        J._ck(J.lib().jsdr_bpsk_read_ds(bank_e.h, J._ptr(h_ds), J.MEM_HOST))         # D2H decimated output
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    ctx.sync()
+    e2e_s = (time.perf_counter() - t0) / a.steps
+    e2e_samples = e_ch * S
+    h2d = h_raw.nbytes
+    d2h = h_psd.nbytes + h_pk.nbytes + h_ds.nbytes
+
+    # ---- reduce over ranks: max time, summed work
+    t_step = ms / a.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_step, fft_ms, mix_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step, fft_ms, mix_ms, e2e_s = [float(x) for x in t.tolist()]
+        cnt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches = int(cnt.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = world * samples / (t_step * 1e-3) / 1e6
+        fft_bytes = samples * 8 + batch * 8            # s16 in (4 B) + float PSD out (4 B) per sample, + 2 floats per block
+        mix_bytes = samples * 4 + samples // D * 16 + samples // 32 * 16   # s16 in + complex double out (+ phase checkpoints r/w)
+        fft_gbs = fft_bytes / (fft_ms * 1e-3) / 1e9
+        mix_gbs = (samples * 4 + samples // D * 16) / (mix_ms * 1e-3) / 1e9
+        step_bytes = samples * 4 + samples * 4 + samples // D * 16
+        line = {
+            "metric": "Msamples/s (complex IQ) through mix+FIR+FFT",
+            "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(t_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (FFT/PSD) + f64 (tuner/decimator, reference order)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "channels_per_gpu": nchan, "blocks_per_channel": nblk,
+                       "fft_n": n, "rate": RATE, "decimation": D, "taps": a.taps,
+                       "l2": "inputs larger than L2 (%.1f GiB resident per GPU)" % (samples * 4 / 2 ** 30),
+                       "sharding": "channels split across ranks, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "fft_kernel (FFT+PSD, s16 in)", "achieved": round(fft_gbs, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(fft_gbs / peak, 4), "traffic": None,
+                         "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json)",
+                         "algorithmic_bytes_per_launch": fft_bytes, "ms_per_launch": round(fft_ms, 4),
+                         "other_kernels": [{"kernel": "k_tuner_scout + k_mixdecim + k_tuner_tail (tuner + decimator)",
+                                            "achieved": round(mix_gbs, 1), "frac": round(mix_gbs / peak, 4),
+                                            "ms_per_launch": round(mix_ms, 4),
+                                            "algorithmic_bytes_per_launch": samples * 4 + samples // D * 16}],
+                         "pipeline": {"algorithmic_bytes_per_step_fused": step_bytes,
+                                      "achieved": round(step_bytes / (t_step * 1e-3) / 1e9, 1),
+                                      "frac": round(step_bytes / (t_step * 1e-3) / 1e9 / peak, 4),
+                                      "note": "4 B in (read once) + 4 B PSD + 16/D B decimated out per sample"}},
+            "e2e": {"value": round(world * e2e_samples / e2e_s / 1e6, 1), "unit": "Msamples/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "sample": f"{e_ch} channels x {nblk} blocks per rank through jsdr_pump_receive_s16 + jsdr_bpsk_read_ds with pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not a.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_pipeline(a, a.cpu_seconds, os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+
+    for h in (f, bank, f_e, bank_e):
+        h.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

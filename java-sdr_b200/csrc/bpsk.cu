@@ -484,6 +484,34 @@ int upload(jsdr_ctx *ctx, void *dst, const void *src, size_t bytes)
     return JSDR_OK;
 }
 
+// Buffers of the 9600 S/s stages, allocated when a receive first needs them (a
+// stages==1 bank, e.g. the mix+FIR benchmark, never pays for them).
+int ensure_stage_buffers(jsdr_bpsk *b)
+{
+    if (b->d_dm_out) return JSDR_OK;
+    jsdr_ctx *ctx = b->ctx;
+    const size_t nc = (size_t)b->nchan;
+    struct { void **p; size_t bytes; } req[] = {
+        {(void **)&b->d_vco_ix, (size_t)b->max_ds},
+        {(void **)&b->d_bit_roll, (size_t)b->max_ds},
+        {(void **)&b->d_dm_hist[0], sizeof(double2) * 64 * nc},
+        {(void **)&b->d_dm_hist[1], sizeof(double2) * 64 * nc},
+        {(void **)&b->d_bits, nc * b->max_bits},
+        {(void **)&b->d_bit_at, sizeof(long long) * nc * b->max_bits},
+        {(void **)&b->d_dm_out, sizeof(double2) * nc * b->max_ds},
+    };
+    for (auto &r : req) {
+        cudaError_t e = cudaMalloc(r.p, r.bytes);
+        if (e != cudaSuccess) {
+            set_error("stage buffers: cudaMalloc(%zu): %s", r.bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return JSDR_ENOMEM;
+        }
+        JSDR_CUDA(cudaMemsetAsync(*r.p, 0, r.bytes, ctx->stream));
+    }
+    return JSDR_OK;
+}
+
 int bpsk_reset_ds(jsdr_bpsk *b)
 {
     jsdr_ctx *ctx = b->ctx;
@@ -518,6 +546,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     const int NO = (b->ds_cnt + S) / D;
     const int n0 = D - 1 - b->ds_cnt;
     const int nchan = b->nchan;
+    if (b->stages >= 2) JSDR_TRY(ensure_stage_buffers(b));
 
     // ---- fork: data-independent phase scouts on the side stream
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -626,6 +655,8 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
             JSDR_TRY(launched(ctx, "k_timing"));
         }
     }
+    if (NO == 0)   // nothing reached the 9600 S/s stage in this call: no bits either
+        JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * nchan, ctx->stream));
     b->cnt_ds += NO;
     if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
@@ -672,14 +703,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_ds_hist[1], sizeof(double2) * kMaxDsTaps * nc);
     ALLOC(b->d_ds_out, sizeof(double2) * nc * b->max_ds);
     ALLOC(b->d_vco_state, sizeof(double) * 2);
-    ALLOC(b->d_vco_ix, (size_t)b->max_ds);
-    ALLOC(b->d_bit_roll, (size_t)b->max_ds);
-    ALLOC(b->d_dm_hist[0], sizeof(double2) * 64 * nc);
-    ALLOC(b->d_dm_hist[1], sizeof(double2) * 64 * nc);
-    ALLOC(b->d_dm_out, sizeof(double2) * nc * b->max_ds);
     ALLOC(b->d_ts, sizeof(TimingState) * nc);
-    ALLOC(b->d_bits, nc * b->max_bits);
-    ALLOC(b->d_bit_at, sizeof(long long) * nc * b->max_bits);
     ALLOC(b->d_nbits, sizeof(int32_t) * nc);
 #undef ALLOC
     // tables and constants, computed on the host exactly as the reference's setup code does
@@ -789,7 +813,7 @@ extern "C" int jsdr_bpsk_read_ds(jsdr_bpsk *b, double *out, int mem) { return re
 
 extern "C" int jsdr_bpsk_read_dm(jsdr_bpsk *b, double *out, int mem)
 {
-    JSDR_REQUIRE(b && b->stages >= 2, JSDR_ESTATE, "matched filter stage is disabled");
+    JSDR_REQUIRE(b && b->stages >= 2 && b->d_dm_out, JSDR_ESTATE, "matched filter stage is disabled or has not run");
     return read_rows(b, b->d_dm_out, out, mem);
 }
 
@@ -797,7 +821,7 @@ extern "C" int jsdr_bpsk_read_bits(jsdr_bpsk *b, int8_t *bits, int64_t *bit_at, 
                                    int max_bits, int mem)
 {
     JSDR_REQUIRE(b && nbits, JSDR_EINVAL, "null argument");
-    JSDR_REQUIRE(b->stages >= 3, JSDR_ESTATE, "bit decision stage is disabled");
+    JSDR_REQUIRE(b->stages >= 3 && b->d_bits, JSDR_ESTATE, "bit decision stage is disabled or has not run");
     JSDR_REQUIRE(max_bits >= 0, JSDR_EINVAL, "negative max_bits");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());

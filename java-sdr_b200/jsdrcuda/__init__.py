@@ -228,9 +228,7 @@ class Context:
         p = C.c_void_p()
         _ck(lib().jsdr_host_alloc(self.h, n * dtype.itemsize, C.byref(p)))
         buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
-        a = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
-        a._jsdr_pinned = p.value  # keep the address for host_free
-        return a
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
     def host_free(self, a: np.ndarray):
         lib().jsdr_host_free(self.h, _vp(a.ctypes.data))
@@ -248,6 +246,22 @@ def device_count() -> int:
     n = C.c_int()
     _ck(lib().jsdr_device_count(C.byref(n)))
     return n.value
+
+
+def design_lowpass(ntaps: int, cutoff_hz: float, rate: int) -> np.ndarray:
+    """Hamming windowed-sinc low-pass by the demod.java:356-366 formula (band
+    -cutoff..+cutoff) in double: the 64-tap decimator shape of BASELINE config 4."""
+    ord_ = ntaps - 1
+    nlo, nhi = -cutoff_hz / rate, cutoff_hz / rate
+    w = np.empty(ntaps, dtype=np.float64)
+    for n in range(ntaps):
+        d = n - ord_ / 2.0
+        if d == 0:
+            w[n] = 2.0 * (nhi - nlo)
+        else:
+            w[n] = (np.sin(2 * np.pi * nhi * d) - np.sin(2 * np.pi * nlo * d)) / (np.pi * d)
+        w[n] *= 0.54 - 0.46 * np.cos(2 * np.pi * n / ord_)
+    return w
 
 
 def fft_supported(n: int) -> bool:

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         _lib.orc_fec_table_probe.restype = C.c_int
         _lib.orc_baseline_fft_s16.restype = C.c_int
         _lib.orc_baseline_mixdecim_s16.restype = C.c_int
+        _lib.orc_baseline_pipeline_s16.restype = C.c_int
     return _lib
 
 
@@ -175,7 +176,7 @@ class _BpskS(C.Structure):
         ("cntFEC", C.c_int64), ("cntDec", C.c_int64),
         ("dmCorr", C.c_int), ("dmMaxCorr", C.c_int), ("dmErrBits", C.c_int), ("decodeOK", C.c_int),
         ("dmFECCorr", C.c_int8 * 5200), ("decoded", C.c_uint8 * 256),
-        ("do_fec", C.c_int), ("doUp", C.c_int),
+        ("do_fec", C.c_int), ("stages", C.c_int), ("doUp", C.c_int),
         ("avePeakPower", C.c_double), ("aveCentreBin", C.c_double), ("centreBin", C.c_int),
         ("sinTab", C.c_double * 256), ("cosTab", C.c_double * 256),
         ("cap_ds", C.POINTER(C.c_double)), ("cap_ds_n", C.c_int), ("cap_ds_max", C.c_int),
@@ -190,11 +191,12 @@ class Bpsk:
     """FUNcubeBPSKDemod.java:366-595 for one tuner."""
 
     def __init__(self, rate: int, tuning: float = 12000.0, do_fec: bool = False,
-                 ds_taps: np.ndarray | None = None):
+                 ds_taps: np.ndarray | None = None, stages: int = 3):
         assert C.sizeof(_BpskS) == lib().orc_bpsk_sizeof(), "struct layout drift"
         self.s = _BpskS()
         lib().orc_bpsk_init(C.byref(self.s), rate, C.c_double(tuning))
         self.s.do_fec = int(do_fec)
+        self.s.stages = stages
         if ds_taps is not None:
             t = np.ascontiguousarray(ds_taps, dtype=np.float64)
             lib().orc_bpsk_set_ds_filter(C.byref(self.s), _p(t, C.c_double), t.size)
@@ -299,3 +301,23 @@ def baseline_mixdecim_s16(raw: np.ndarray, nchan: int, rate: int, tuning: np.nda
                                            _p(tuning, C.c_double), tp, nt,
                                            _p(out, C.c_double), nthreads)
     return out, used
+
+
+def baseline_pipeline_s16(raw: np.ndarray, nchan: int, nblocks: int, n: int, rate: int,
+                          tuning: np.ndarray, taps: np.ndarray | None, nthreads: int):
+    """The benchmark pipeline on the CPU: per (channel, block) JavaAudio conversion,
+    fft.receive (plan rebuilt per block, fft.java:194) and tuner + decimator."""
+    raw = np.ascontiguousarray(raw, dtype=np.int16).ravel()
+    assert raw.size == nchan * nblocks * n * 2
+    D = rate // 9600
+    tuning = np.ascontiguousarray(tuning, dtype=np.float64)
+    psd = np.empty((nchan * nblocks, n + 2), dtype=np.float32)
+    ds = np.zeros((nchan, nblocks * n // D, 2), dtype=np.float64)
+    tp, nt = None, 0
+    if taps is not None:
+        taps = np.ascontiguousarray(taps, dtype=np.float64)
+        tp, nt = _p(taps, C.c_double), taps.size
+    used = lib().orc_baseline_pipeline_s16(_p(raw, C.c_int16), nchan, nblocks, n, rate,
+                                           _p(tuning, C.c_double), tp, nt,
+                                           _p(psd, C.c_float), _p(ds, C.c_double), nthreads)
+    return psd, ds, used

@@ -477,6 +477,7 @@ void orc_bpsk_init(orc_bpsk *s, int rate, double tuning)
     s->dsPos = s->ds_ntaps - 1;                     /* :468 */
     s->dmPos = MATCHED_FILTER_SIZE - 1;             /* :496 */
     s->dmEnergyOut = 1.0;                           /* :499 */
+    s->stages = 3;
     orc_bpsk_set_tuning(s, tuning);
 }
 
@@ -600,7 +601,16 @@ static void RxDownSample(orc_bpsk *s, double i, double q)
             fq += s->dsBuf[dsi][1] * s->dsFilter[n];
         }
         s->dsCnt = 0;
-        RxDemodulate(s, fi * HOWARD_FUDGE_FACTOR, fq * HOWARD_FUDGE_FACTOR);
+        if (s->stages >= 2) {
+            RxDemodulate(s, fi * HOWARD_FUDGE_FACTOR, fq * HOWARD_FUDGE_FACTOR);
+        } else {
+            if (s->cap_ds && s->cap_ds_n < s->cap_ds_max) {
+                s->cap_ds[2 * s->cap_ds_n] = fi * HOWARD_FUDGE_FACTOR;
+                s->cap_ds[2 * s->cap_ds_n + 1] = fq * HOWARD_FUDGE_FACTOR;
+                s->cap_ds_n++;
+            }
+            s->cntDS++;
+        }
     }
     s->dsPos--;
     if (s->dsPos < 0) s->dsPos = s->ds_ntaps - 1;
@@ -1106,8 +1116,9 @@ typedef struct {
     int tid, nthreads;
     /* fft job */
     const int16_t *raw; int nblocks, n, rate; float *psd;
-    /* mixdecim job */
+    /* mixdecim / pipeline job */
     int nchan, nsamples; const double *tuning, *taps; int ntaps; double *out;
+    int stages;
 } job_t;
 
 static void *fft_worker(void *arg)
@@ -1131,6 +1142,7 @@ static void *mixdecim_worker(void *arg)
     float *buf = (float *)malloc(sizeof(float) * 2 * 4096);
     for (int c = j->tid; c < j->nchan; c += j->nthreads) {
         orc_bpsk_init(s, j->rate, j->tuning[c]);
+        s->stages = j->stages;
         if (j->taps) orc_bpsk_set_ds_filter(s, j->taps, j->ntaps);
         s->cap_ds = j->out + (size_t)c * nout * 2;
         s->cap_ds_max = nout;
@@ -1177,6 +1189,43 @@ int orc_baseline_mixdecim_s16(const int16_t *raw, int nchan, int nsamples, int r
     job_t j;
     memset(&j, 0, sizeof(j));
     j.raw = raw; j.nchan = nchan; j.nsamples = nsamples; j.rate = rate;
-    j.tuning = tuning; j.taps = taps; j.ntaps = ntaps; j.out = out;
+    j.tuning = tuning; j.taps = taps; j.ntaps = ntaps; j.out = out; j.stages = 1;
     return run_jobs(mixdecim_worker, &j, nthreads);
+}
+
+static void *pipeline_worker(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    const int n = j->n, D = j->rate / 9600;
+    const int nout = (j->nblocks * n) / D;
+    orc_bpsk *s = (orc_bpsk *)malloc(sizeof(orc_bpsk));
+    float *buf = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+    for (int c = j->tid; c < j->nchan; c += j->nthreads) {
+        orc_bpsk_init(s, j->rate, j->tuning[c]);
+        s->stages = 1;
+        if (j->taps) orc_bpsk_set_ds_filter(s, j->taps, j->ntaps);
+        s->cap_ds = j->out + (size_t)c * nout * 2;
+        s->cap_ds_max = nout;
+        s->cap_ds_n = 0;
+        for (int b = 0; b < j->nblocks; b++) {
+            /* JavaAudio.run: convert once, then fan out to the handlers (:276-304) */
+            orc_s16_to_float(j->raw + ((size_t)c * j->nblocks + b) * 2 * n, n, 2, 0, 0, buf);
+            orc_fft_receive_f32plan(buf, n, j->rate, j->psd + ((size_t)c * j->nblocks + b) * (n + 2), NULL);
+            orc_bpsk_receive(s, buf, n);
+        }
+    }
+    free(s);
+    free(buf);
+    return NULL;
+}
+
+int orc_baseline_pipeline_s16(const int16_t *raw, int nchan, int nblocks, int n, int rate,
+                              const double *tuning, const double *taps, int ntaps,
+                              float *psd, double *ds, int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.raw = raw; j.nchan = nchan; j.nblocks = nblocks; j.n = n; j.rate = rate;
+    j.tuning = tuning; j.taps = taps; j.ntaps = ntaps; j.psd = psd; j.out = ds;
+    return run_jobs(pipeline_worker, &j, nthreads);
 }

@@ -104,6 +104,7 @@ typedef struct {
     int8_t dmFECCorr[5200];
     uint8_t decoded[256];
     int do_fec;                 /* run the sync correlator + FECDecode (f-1) */
+    int stages;                 /* 1: stop after RxDownSample (CPU baseline of mix+FIR); 3: full chain */
     /* auto-tune (doBufferFFT) */
     int doUp;
     double avePeakPower, aveCentreBin;
@@ -134,6 +135,12 @@ int  orc_fec_table_probe(int which, int idx);                     /* table self-
 /* ---- CPU baseline drivers (pthreads over channels / blocks) ------------ */
 /* returns the number of threads used */
 int orc_baseline_fft_s16(const int16_t *raw, int nblocks, int n, int rate, float *psd, int nthreads);
+/* the benchmark pipeline per (channel, block): JavaAudio conversion, fft.receive
+ * (float plan rebuilt per block) and the tuner + decimator */
+int orc_baseline_pipeline_s16(const int16_t *raw, int nchan, int nblocks, int n, int rate,
+                              const double *tuning, const double *taps, int ntaps,
+                              float *psd /* nchan*nblocks*(n+2) */, double *ds /* nchan*(nblocks*n/D)*2 */,
+                              int nthreads);
 int orc_baseline_mixdecim_s16(const int16_t *raw, int nchan, int nsamples, int rate,
                               const double *tuning, const double *taps, int ntaps,
                               double *out /* nchan * (nsamples/D) * 2 */, int nthreads);
