@@ -267,7 +267,7 @@ def main():
     h_raw = ctx.host_alloc((e_ch, 2 * S), np.int16)
     h_psd = ctx.host_alloc((e_batch, n + 2), np.float32)
     h_pk = ctx.host_alloc((e_batch,), np.int32)
-    h_ds = ctx.host_alloc((e_ch, S // D, 2), np.float64)
+    h_ds = ctx.host_alloc((e_ch, S // D + 1, 2), np.float64)   # the carry makes the count vary by one per call
     h_raw[:] = tile[np.arange(e_ch) % tile_ch]
     def e2e_step():
         J.pump_receive_s16(f_e, bank_e, h_raw, nblk, h_psd, h_pk, mem=J.MEM_HOST)   # H2D raw, D2H PSD inside

@@ -29,7 +29,11 @@ namespace bpsk {
 constexpr double kTwoPi = 2.0 * 3.141592653589793;       // Java 2.0*Math.PI
 constexpr double kInvTwoPi = 1.0 / kTwoPi;
 constexpr int kTileOut = 128;                            // decimator outputs per CTA
-constexpr int kTileThreads = 256;                        // 128 outputs x {I,Q}
+constexpr int kTileThreads = 128;                        // one thread per output in the FIR phase
+constexpr int kPrefetch = 21;                            // raw samples held per thread (covers D <= 20, 128 taps)
+// 256/(2*pi) for the double constant 2.0*Math.PI, split hi + lo (host long double)
+constexpr double kIdxScaleHi = 40.74366543152521;
+constexpr double kIdxScaleLo = -9.306125250357089e-16;
 constexpr int kDmTile = 128;                             // matched-filter outputs per CTA
 
 enum { FMT_F32 = 0, FMT_S16 = 1 };
@@ -62,9 +66,9 @@ static const float kDmFilterF[65] = {
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ double phase_step(double p, double inc)
 {   // :384-386 / :511-513  p += inc; if (p > 2pi) p -= 2pi
-    p = __dadd_rn(p, inc);
-    if (p > kTwoPi) p = __dadd_rn(p, -kTwoPi);
-    return p;
+    const double a = __dadd_rn(p, inc);
+    const double w = __dadd_rn(a, -kTwoPi);      // speculative, off the compare's path
+    return (a > kTwoPi) ? w : a;
 }
 
 // (int)(p*256.0/(2.0*Math.PI)) % 256 for p > 0 (:389).  The division is replaced
@@ -72,11 +76,14 @@ __device__ __forceinline__ double phase_step(double p, double inc)
 // IEEE division the reference performs decides.
 __device__ __forceinline__ int table_index(double p)
 {
-    double t = __dmul_rn(p, 256.0);
-    double a = t * kInvTwoPi;
-    int k;
-    if (fabs(a - rint(a)) < 1e-9) k = __double2int_rz(__ddiv_rn(t, kTwoPi));
-    else k = __double2int_rz(a);
+    const double t = __dmul_rn(p, 256.0);
+    // a*2^20 + 1.5*2^52: the low word of the sum is round(a*2^20) (a < 2^9)
+    const double y = __fma_rn(t, kInvTwoPi * 1048576.0, 6755399441055744.0);
+    const int yi = __double2loint(y);
+    const int frac = yi & 0xfffff;
+    int k = yi >> 20;
+    if (frac < 64 || frac > 1048576 - 64)       // within 6e-5 of an integer: decide exactly
+        k = __double2int_rz(__ddiv_rn(t, kTwoPi));
     return k & 255;
 }
 
@@ -86,6 +93,17 @@ template <>
 struct RawT<FMT_F32> { typedef float2 type; };
 template <>
 struct RawT<FMT_S16> { typedef uint32_t type; };
+
+// (float)s / 32767f, correctly rounded, without the generic division: q0 = s*r,
+// e = fma(-q0, 32767, s), q = fma(r, e, q0) with r = fl(1/32767).  Checked
+// exhaustively against IEEE division for all 65536 inputs (tests/test_oracle.py).
+__device__ __forceinline__ float s16_over_32767(float x)
+{
+    const float r = 3.0518509447574615e-05f;
+    const float q0 = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q0, 32767.0f, x);
+    return __fmaf_rn(r, e, q0);
+}
 
 template <int FMT>
 __device__ __forceinline__ void raw_to_iq(typename RawT<FMT>::type w, int ic, int qc, double &i, double &q)
@@ -97,28 +115,37 @@ __device__ __forceinline__ void raw_to_iq(typename RawT<FMT>::type w, int ic, in
         // JavaAudio.java:281-288: s += (short)ic (16-bit wrap); (float)s/(float)Short.MAX_VALUE
         short si = (short)((int)(w & 0xffffu) + ic);
         short sq = (short)((int)(w >> 16) + qc);
-        i = (double)__fdiv_rn((float)si, 32767.0f);
-        q = (double)__fdiv_rn((float)sq, 32767.0f);
+        i = (double)s16_over_32767((float)si);
+        q = (double)s16_over_32767((float)sq);
     }
 }
 
 // ------------------------------------------------------------------ scouts
-// One thread per channel replays tuPhase over the block and leaves the phase
-// before every kChunk-th sample.  Data independent: runs on the side stream.
-__global__ void k_tuner_scout(const double *__restrict__ inc_, double *__restrict__ phase_,
-                              double *__restrict__ chunk_phase, int nchan, int S)
+// The tuner phase is data independent but must be replayed add by add to stay
+// bit-exact.  That serial chain (about 25 cycles per step) is all this kernel does:
+// one lane per channel steps the phase through the block and leaves a checkpoint
+// (the phase before the first sample) for every 32-sample chunk.  It runs on the
+// side stream, one block ahead of the data (see bpsk_receive), and costs almost no
+// issue slots, so it hides behind the data kernels.
+__global__ void __launch_bounds__(32)
+k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_in,
+              double *__restrict__ phase_out, double *__restrict__ ckpt, int nchan, int S)
 {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.x * 32 + threadIdx.x;
     if (ch >= nchan) return;
-    double p = phase_[ch];
+    double p = phase_in[ch];
     const double inc = inc_[ch];
-    int nchunks = (S + kChunk - 1) / kChunk;
-    for (int c = 0; c < nchunks; c++) {
-        chunk_phase[(size_t)c * nchan + ch] = p;
-        int steps = min(kChunk, S - c * kChunk);
-        for (int s = 0; s < steps; s++) p = phase_step(p, inc);
+    const int nfull = S >> 5;
+    for (int w = 0; w < nfull; w++) {
+        ckpt[(size_t)w * nchan + ch] = p;
+#pragma unroll
+        for (int j = 0; j < 32; j++) p = phase_step(p, inc);
     }
-    phase_[ch] = p;
+    if (S & 31) {
+        ckpt[(size_t)nfull * nchan + ch] = p;
+        for (int j = 0; j < (S & 31); j++) p = phase_step(p, inc);
+    }
+    phase_out[ch] = p;
 }
 
 // vcoPhase (:511-516) and dmBitPhase (:581-584) are the same for every channel of
@@ -156,137 +183,169 @@ struct MixParams {
     long long chan_stride;     // complex samples between channels (0: shared stream)
     int S;                     // samples in this block
     int ic, qc;
-    const double *tu_inc;
-    const double *chunk_phase;
+    const double *tu_inc;      // [nchan]
+    const unsigned long long *tu_dx;   // [nchan] index step in 2^-48 units (0: use the exact path)
+    const double *ckpt;        // [chunks][nchan] tuner phase before each 32-sample chunk
     int nchan;
     const double2 *hist_in;    // [nchan][kMaxDsTaps], entry k is local sample k-H
     double2 *hist_out;
-    const double *taps;
     int ntaps;
-    const double *cossin;
+    const double2 *cossin;     // [257] (cos, sin) pairs; entry 256 = (1, 1) for the bypass case
     int D, n0, NO;             // first output's local sample index, outputs this block
+    unsigned magicD;           // 2^32/D + 1: i/D == __umulhi(i, magicD) for i, D < 65536
+    int pad;                   // 1: one pad slot per D samples (even D), 0: none
+    int ix_off;                // byte offset of the index array in dynamic shared memory
     double2 *ds_out;
     int max_ds;
+    // in the parameter (constant) bank, read with uniform loads:
+    double taps[kMaxDsTaps];
+    int off[kMaxDsTaps];       // byte offset of tap k's sample from the thread's base slot
 };
 
-// Window index -> shared-memory slot.  For even D one pad slot is inserted per D
-// samples so that the decimating reads (lanes D apart) have an odd stride.
-// i / D is done as a multiply-high: exact for i, D < 65536 with magic = 2^32/D + 1.
-__device__ __forceinline__ int mix_pad(int i, int D, unsigned magic)
-{
-    return (D & 1) ? i : i + (int)__umulhi((unsigned)i, magic);
-}
+// table index of one tuner step, 256 = bypass (phase <= 0: RxDownSample(i, q), :395)
+__device__ __forceinline__ int tuner_index(double ph) { return (ph > 0.0) ? table_index(ph) : 256; }
 
-// shared-memory carve-up for k_mixdecim (all offsets in bytes, 16-aligned)
-struct MixSmem {
-    int span_pad, raw_n;
-    unsigned magic;
-    size_t off_I, off_Q, off_tab, off_taps, off_raw, total;
-};
-static MixSmem mix_smem_layout(int D, int ntaps, int fmt)
-{
-    MixSmem L;
-    int span = kTileOut * D + ntaps + 1;
-    L.span_pad = ((D & 1) ? span : span + span / D) + 2;
-    L.magic = (unsigned)(4294967296ULL / (unsigned)D) + 1u;
-    int chunks = (kTileOut * D + ntaps) / kChunk + 3;
-    L.raw_n = chunks * (kChunk + 1);
-    size_t o = 0;
-    L.off_I = o; o += sizeof(double) * L.span_pad;
-    L.off_Q = o; o += sizeof(double) * L.span_pad;
-    L.off_tab = o; o += sizeof(double) * 512;
-    L.off_taps = o; o += sizeof(double) * kMaxDsTaps;
-    L.off_raw = o; o += (fmt == FMT_S16 ? 4 : 8) * (size_t)L.raw_n;
-    L.total = (o + 15) & ~(size_t)15;
-    return L;
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(kTileThreads)
-k_mixdecim(const MixParams p, const MixSmem L)
+// One CTA = one channel x kTileOut outputs, four phases:
+//   1  chunk threads replay the 32 phase steps of their chunk from the scout's
+//      checkpoint and leave only the table index of each sample (:384-390);
+//   2  every sample of the window is converted and mixed once, sample parallel with
+//      coalesced loads (:389-390), into shared memory with one pad slot per D samples
+//      so that lanes D apart fall in different banks;
+//   3  the decimating FIR (:477-486), newest sample first, one thread per output,
+//      one 16-byte load per tap.  With NTAPS/DD fixed at compile time the tap
+//      offsets are immediates and the taps come straight from the constant bank.
+template <int FMT, int NTAPS, int DD>
+__global__ void __launch_bounds__(kTileThreads, 4) k_mixdecim(const MixParams p)
 {
     typedef typename RawT<FMT>::type raw_t;
     extern __shared__ __align__(16) unsigned char smem[];
-    double *sI = reinterpret_cast<double *>(smem + L.off_I);
-    double *sQ = reinterpret_cast<double *>(smem + L.off_Q);
-    double *sTab = reinterpret_cast<double *>(smem + L.off_tab);
-    double *sTaps = reinterpret_cast<double *>(smem + L.off_taps);
-    raw_t *sRaw = reinterpret_cast<raw_t *>(smem + L.off_raw);
+    double2 *sM = reinterpret_cast<double2 *>(smem);
+    uint16_t *sIx = reinterpret_cast<uint16_t *>(smem + p.ix_off);   // window index i lives at i+32 (+ one pad per 32)
+    __shared__ double2 sTab[257];
 
     const int tid = threadIdx.x;
     const int ch = blockIdx.y;
     const int m0 = blockIdx.x * kTileOut;
     const int cnt = min(kTileOut, p.NO - m0);
-    const int D = p.D, H = p.ntaps - 1;
-    const int n_hi = p.n0 + (m0 + cnt - 1) * D;       // newest sample this tile needs
-    const int n_lo = p.n0 + m0 * D - H;               // oldest (negative: history)
-    const int c_lo = max(n_lo, 0) / kChunk;
-    const int c_hi = n_hi / kChunk;
-    const int r0 = c_lo * kChunk;
+    const int D = DD ? DD : p.D;
+    const int ntaps = NTAPS ? NTAPS : p.ntaps;
+    const int H = ntaps - 1;
+    const int pad = DD ? ((DD & 1) ? 0 : 1) : p.pad;
+    const int n_lo = p.n0 + m0 * D - H;               // oldest sample needed (negative: history)
+    const int span = (cnt - 1) * D + ntaps;           // window length
+    const int i0 = max(-n_lo, 0);                     // first window index that is in this block
 
-    for (int i = tid; i < 512; i += kTileThreads) sTab[i] = p.cossin[i];
-    for (int i = tid; i < p.ntaps; i += kTileThreads) sTaps[i] = p.taps[i];
-
-    // coalesced raw load, one pad word per chunk
-    {
-        const raw_t *src = reinterpret_cast<const raw_t *>(p.in) + (long long)ch * p.chan_stride;
-        int r_end = min((c_hi + 1) * kChunk, p.S) - r0;
-        for (int r = tid; r < r_end; r += kTileThreads) sRaw[r + r / kChunk] = src[r0 + r];
-    }
-    // history part of the window (samples before this block)
-    if (n_lo < 0) {
-        const double2 *h = p.hist_in + (size_t)ch * kMaxDsTaps;
-        for (int ii = tid; ii < -n_lo; ii += kTileThreads) {
-            double2 v = h[n_lo + ii + H];
-            int f = mix_pad(ii, D, L.magic);
-            sI[f] = v.x;
-            sQ[f] = v.y;
+    for (int i = tid; i < 257; i += kTileThreads) sTab[i] = p.cossin[i];
+    if (n_lo < 0) {                                   // window reaches into the previous block
+        const double2 *hist = p.hist_in + (size_t)ch * kMaxDsTaps;
+        for (int i = tid; i < i0; i += kTileThreads) {
+            const int q = pad ? (int)__umulhi((unsigned)i, p.magicD) : 0;
+            sM[i + q] = hist[n_lo + i + H];
         }
     }
-    __syncthreads();
+    // raw samples of this thread's phase-2 work, fetched now so the loads are in
+    // flight while phase 1 computes
+    const raw_t *src = reinterpret_cast<const raw_t *>(p.in) + (long long)ch * p.chan_stride + n_lo;
+    raw_t pre[kPrefetch];
+#pragma unroll
+    for (int r = 0; r < kPrefetch; r++) {
+        const int i = i0 + tid + r * kTileThreads;
+        if (i < span) pre[r] = src[i];
+    }
 
-    // mix: one thread per checkpoint chunk, phase replayed exactly (:384-396)
-    {
+    {   // phase 1: table indices, one thread per 32-sample chunk
         const double inc = p.tu_inc[ch];
+        const unsigned long long dx = p.tu_dx[ch];
+        const int c_lo = (n_lo + i0) >> 5, c_hi = (n_lo + span - 1) >> 5;
         for (int c = c_lo + tid; c <= c_hi; c += kTileThreads) {
-            double ph = p.chunk_phase[(size_t)c * p.nchan + ch];
-            const raw_t *rw = sRaw + (c - c_lo) * (kChunk + 1);
-            int n = c * kChunk;
-            const int s_end = min(kChunk, p.S - n);
-            for (int s = 0; s < s_end; s++, n++) {
-                ph = phase_step(ph, inc);
-                const int ii = n - n_lo;               // window index of sample n
-                if (ii < 0 || n > n_hi) continue;      // outside the window: only the phase advances
-                double xi, xq;
-                raw_to_iq<FMT>(rw[s], p.ic, p.qc, xi, xq);
-                if (ph > 0.0) {                         // :388
-                    int ix = table_index(ph);
-                    xi = __dmul_rn(xi, sTab[ix]);        // i*cosTab[ix]
-                    xq = __dmul_rn(xq, sTab[256 + ix]);  // q*sinTab[ix]
+            const double ph0 = p.ckpt[(size_t)c * p.nchan + ch];
+            const int ibase = (c << 5) - n_lo;        // window index of the chunk's first sample
+            const int steps = min(32, p.S - (c << 5));
+            // (edge chunks hang over the window; the index array has a 32-entry margin at
+            // both ends so they take the same unguarded path)
+            bool exact = !(dx != 0ull && ph0 >= 0.0);
+            if (!exact) {
+                // Fast path.  x = phase*256/2pi as 8.48 fixed point, anchored at the exact
+                // checkpoint and advanced by integer adds.  Over 32 steps the reference's
+                // accumulated rounding moves the true value by < 2^-39, so the integer part
+                // is the reference's index unless x is within 2^-16 of an integer; then the
+                // chunk is redone with the reference's own arithmetic.
+                const double hi = __dmul_rn(ph0, kIdxScaleHi);
+                const double lo = __fma_rn(ph0, kIdxScaleLo, __fma_rn(ph0, kIdxScaleHi, -hi));
+                unsigned long long x = (unsigned long long)(__double2ll_rn(hi * 281474976710656.0) +
+                                                            __double2ll_rn(lo * 281474976710656.0));
+                unsigned near = 0;
+                const int ib = ibase + 32;
+                uint16_t *dst = sIx + ib + (ib >> 5);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    x += dx;
+                    const unsigned xh = (unsigned)(x >> 32);
+                    near |= ((xh + 1u) & 0xffffu) <= 1u;
+                    dst[j + ((((ib & 31) + j) >> 5))] = (uint16_t)((xh >> 16) & 255u);
                 }
-                int f = mix_pad(ii, D, L.magic);
-                sI[f] = xi;
-                sQ[f] = xq;
+                exact = near != 0u;
+            }
+            if (exact) {                              // reference arithmetic, step by step
+                double ph = ph0;
+                for (int j = 0; j < steps; j++) {
+                    ph = phase_step(ph, inc);
+                    const int i = ibase + j;
+                    if (i >= i0 && i < span) sIx[i + 32 + ((i + 32) >> 5)] = (uint16_t)tuner_index(ph);
+                }
             }
         }
     }
     __syncthreads();
 
-    // decimating FIR (:477-486): newest sample first, one thread per output and component
-    {
-        const int lane_out = tid & (kTileOut - 1);
-        const int comp = tid / kTileOut;               // 0: I, 1: Q (warp uniform)
-        if (lane_out < cnt) {
-            const double *sX = comp ? sQ : sI;
-            const int top = (p.n0 + (m0 + lane_out) * D) - n_lo;
-            double acc = 0.0;
-            for (int k = 0; k < p.ntaps; k++)
-                acc = __dadd_rn(acc, __dmul_rn(sX[mix_pad(top - k, D, L.magic)], sTaps[k]));
-            // :469,486  fi * HOWARD_FUDGE_FACTOR, with 0.9*32768.0 folded by javac to one double
-            double outv = __dmul_rn(acc, 0.9 * 32768.0);
-            double *o = reinterpret_cast<double *>(p.ds_out + (size_t)ch * p.max_ds + m0 + lane_out);
-            o[comp] = outv;
+    {   // phase 2: convert + mix, sample parallel
+#pragma unroll
+        for (int r = 0; r < kPrefetch; r++) {
+            const int i = i0 + tid + r * kTileThreads;
+            if (i < span) {
+                double xi, xq;
+                raw_to_iq<FMT>(pre[r], p.ic, p.qc, xi, xq);
+                const double2 cs = sTab[sIx[i + 32 + ((i + 32) >> 5)]];
+                const int q = pad ? (int)__umulhi((unsigned)i, p.magicD) : 0;
+                sM[i + q] = make_double2(__dmul_rn(xi, cs.x), __dmul_rn(xq, cs.y));   // i*cosTab[ix], q*sinTab[ix]
+            }
         }
+        for (int i = i0 + tid + kPrefetch * kTileThreads; i < span; i += kTileThreads) {   // very wide windows only
+            double xi, xq;
+            raw_to_iq<FMT>(src[i], p.ic, p.qc, xi, xq);
+            const double2 cs = sTab[sIx[i + 32 + ((i + 32) >> 5)]];
+            const int q = pad ? (int)__umulhi((unsigned)i, p.magicD) : 0;
+            sM[i + q] = make_double2(__dmul_rn(xi, cs.x), __dmul_rn(xq, cs.y));
+        }
+    }
+    __syncthreads();
+
+    if (tid < cnt) {   // phase 3
+        // window index of tap k is tid*D + H - k -> slot tid*(D+pad) + (H-k) + pad*((H-k)/D)
+        const unsigned char *base = smem + (size_t)tid * (D + pad) * sizeof(double2);
+        double ai = 0.0, aq = 0.0;
+        if constexpr (NTAPS > 0 && DD > 0) {
+#pragma unroll
+            for (int k = 0; k < NTAPS; k++) {
+                constexpr int PADC = (DD & 1) ? 0 : 1;
+                const int d = NTAPS - 1 - k;
+                const double2 x = *reinterpret_cast<const double2 *>(base + sizeof(double2) * (d + PADC * (d / DD)));
+                const double h = p.taps[k];
+                ai = __dadd_rn(ai, __dmul_rn(x.x, h));
+                aq = __dadd_rn(aq, __dmul_rn(x.y, h));
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < ntaps; k++) {
+                const double2 x = *reinterpret_cast<const double2 *>(base + p.off[k]);
+                const double h = p.taps[k];
+                ai = __dadd_rn(ai, __dmul_rn(x.x, h));
+                aq = __dadd_rn(aq, __dmul_rn(x.y, h));
+            }
+        }
+        // :469,486  fi * HOWARD_FUDGE_FACTOR, 0.9*32768.0 folded by javac to one double
+        p.ds_out[(size_t)ch * p.max_ds + m0 + tid] =
+            make_double2(__dmul_rn(ai, 0.9 * 32768.0), __dmul_rn(aq, 0.9 * 32768.0));
     }
 }
 
@@ -296,11 +355,8 @@ template <int FMT>
 __global__ void k_tuner_tail(const MixParams p)
 {
     typedef typename RawT<FMT>::type raw_t;
-    __shared__ double sTab[512];
     const int ch = blockIdx.x;
     const int H = p.ntaps - 1;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) sTab[i] = p.cossin[i];
-    __syncthreads();
     const int k = threadIdx.x;
     if (k >= H) return;
     const int n = p.S - H + k;
@@ -309,18 +365,13 @@ __global__ void k_tuner_tail(const MixParams p)
         v = p.hist_in[(size_t)ch * kMaxDsTaps + k + p.S];
     } else {
         const raw_t *src = reinterpret_cast<const raw_t *>(p.in) + (long long)ch * p.chan_stride;
-        int c = n / kChunk;
-        double ph = p.chunk_phase[(size_t)c * p.nchan + ch];
+        double ph = p.ckpt[(size_t)(n >> 5) * p.nchan + ch];
         const double inc = p.tu_inc[ch];
-        for (int s = c * kChunk; s <= n; s++) ph = phase_step(ph, inc);
+        for (int j = n & ~31; j <= n; j++) ph = phase_step(ph, inc);
+        const double2 cs = p.cossin[tuner_index(ph)];
         double xi, xq;
         raw_to_iq<FMT>(src[n], p.ic, p.qc, xi, xq);
-        if (ph > 0.0) {
-            int ix = table_index(ph);
-            xi = __dmul_rn(xi, sTab[ix]);
-            xq = __dmul_rn(xq, sTab[256 + ix]);
-        }
-        v = make_double2(xi, xq);
+        v = make_double2(__dmul_rn(xi, cs.x), __dmul_rn(xq, cs.y));
     }
     p.hist_out[(size_t)ch * kMaxDsTaps + k] = v;
 }
@@ -484,6 +535,32 @@ int upload(jsdr_ctx *ctx, void *dst, const void *src, size_t bytes)
     return JSDR_OK;
 }
 
+// Per-sample advance of x = phase*256/(2*pi) in 2^-48 units, modulo 256, in extended
+// precision (used by k_mixdecim's integer fast path).  0 selects the exact path:
+// non-positive or non-finite increments (mixer bypass, :388).
+unsigned long long index_step_fixed(double inc)
+{
+    if (!(inc > 0.0) || !(inc < 1e6)) return 0ull;
+    const long double c = 256.0L / (long double)(2.0 * M_PI);
+    long double d = fmodl((long double)inc * c, 256.0L);
+    unsigned long long v = (unsigned long long)(d * 281474976710656.0L + 0.5L);
+    return v ? v : 1ull;
+}
+
+// Replay the tuner phase over the next S samples from the committed phase into `P`
+// (side stream).
+int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
+{
+    jsdr_ctx *ctx = b->ctx;
+    k_tuner_scout<<<(b->nchan + 31) / 32, 32, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+                                                             b->nchan, S);
+    JSDR_TRY(launched(ctx, "k_tuner_scout"));
+    JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
+    P.S = S;
+    P.valid = true;
+    return JSDR_OK;
+}
+
 // Buffers of the 9600 S/s stages, allocated when a receive first needs them (a
 // stages==1 bank, e.g. the mix+FIR benchmark, never pays for them).
 int ensure_stage_buffers(jsdr_bpsk *b)
@@ -548,11 +625,12 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     const int nchan = b->nchan;
     if (b->stages >= 2) JSDR_TRY(ensure_stage_buffers(b));
 
-    // ---- fork: data-independent phase scouts on the side stream
+    // ---- fork: data-independent work on the side stream.  The tuner plan for this
+    // block was normally computed while the previous block was being processed.
+    jsdr_bpsk::TunerPlan &P = b->plan[b->plan_cur];
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    k_tuner_scout<<<(nchan + 127) / 128, 128, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, b->d_chunk_phase, nchan, S);
-    JSDR_TRY(launched(ctx, "k_tuner_scout"));
+    if (!(P.valid && P.S == S)) JSDR_TRY(launch_scout(b, P, S));
     if (b->stages >= 2 && NO > 0) {
         const double vco_inc = 2.0 * M_PI * 1200.0 / (double)9600;      // :88
         const double bit_inc = 1.0 / (double)9600, bit_time = 1.0 / (double)1200;   // :91-92
@@ -577,6 +655,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         d_in = b->d_in;
     }
     if (after_input) JSDR_TRY(after_input(user, d_in));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ready, 0));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 
     // ---- tuner + decimator
@@ -587,32 +666,59 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     mp.ic = ic;
     mp.qc = qc;
     mp.tu_inc = b->d_tu_inc;
-    mp.chunk_phase = b->d_chunk_phase;
+    mp.tu_dx = b->d_tu_dx;
+    mp.ckpt = P.ckpt;
     mp.nchan = nchan;
     mp.hist_in = b->d_ds_hist[b->ds_hist_cur];
     mp.hist_out = b->d_ds_hist[b->ds_hist_cur ^ 1];
-    mp.taps = b->d_taps;
     mp.ntaps = b->ntaps;
-    mp.cossin = b->d_cossin;
+    mp.cossin = b->d_cossin2;
     mp.D = D;
     mp.n0 = n0;
     mp.NO = NO;
+    mp.magicD = (unsigned)(4294967296ULL / (unsigned)D) + 1u;
+    mp.pad = (D & 1) ? 0 : 1;          // even D: one pad slot per D samples makes the lane stride odd
     mp.ds_out = b->d_ds_out;
     mp.max_ds = b->max_ds;
-    if (NO > 0) {
-        MixSmem L = mix_smem_layout(D, b->ntaps, FMT);
-        static size_t attr_set[2] = {0, 0};
-        if (attr_set[FMT] < L.total) {
-            JSDR_CUDA(cudaFuncSetAttribute(k_mixdecim<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-            attr_set[FMT] = L.total;
+    memcpy(mp.taps, b->h_taps, sizeof(mp.taps));
+    {
+        const int H = b->ntaps - 1;
+        for (int k = 0; k < kMaxDsTaps; k++) {
+            const int d = (k <= H) ? H - k : 0;
+            mp.off[k] = (int)sizeof(double2) * (d + mp.pad * (d / D));
         }
+    }
+    if (NO > 0) {
+        const int span = (kTileOut - 1) * D + b->ntaps;
+        const size_t m_bytes = sizeof(double2) * (size_t)(span + mp.pad * (span / D) + 2);
+        mp.ix_off = (int)m_bytes;
+        const size_t smem = m_bytes + sizeof(uint16_t) * (size_t)(span + 64 + (span + 64) / 32 + 4);
         dim3 grid((NO + kTileOut - 1) / kTileOut, nchan);
-        k_mixdecim<FMT><<<grid, kTileThreads, L.total, ctx->stream>>>(mp, L);
+        // compile-time (taps, D) for the shapes that matter; anything else runs the generic loop
+        void (*kern)(const MixParams) = k_mixdecim<FMT, 0, 0>;
+        if (b->ntaps == 27 && D == 10) kern = k_mixdecim<FMT, 27, 10>;
+        else if (b->ntaps == 27 && D == 20) kern = k_mixdecim<FMT, 27, 20>;
+        else if (b->ntaps == 64 && D == 20) kern = k_mixdecim<FMT, 64, 20>;
+        JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTileThreads, smem, ctx->stream>>>(mp);
         JSDR_TRY(launched(ctx, "k_mixdecim"));
     }
     if (b->ntaps > 1) {
         k_tuner_tail<FMT><<<nchan, 128, 0, ctx->stream>>>(mp);
         JSDR_TRY(launched(ctx, "k_tuner_tail"));
+    }
+    // this plan is consumed: its end phase becomes the committed phase, and the
+    // scout starts on the next block (same length assumed) while the rest of this
+    // one is still in flight
+    JSDR_CUDA(cudaEventRecord(P.consumed, ctx->stream));
+    P.used = true;
+    P.valid = false;
+    b->d_tu_phase = P.phase_end;
+    b->plan_cur ^= 1;
+    {
+        jsdr_bpsk::TunerPlan &Pn = b->plan[b->plan_cur];
+        if (Pn.used) JSDR_CUDA(cudaStreamWaitEvent(ctx->side, Pn.consumed, 0));
+        JSDR_TRY(launch_scout(b, Pn, S));
     }
     b->ds_hist_cur ^= 1;
     b->ds_cnt = (b->ds_cnt + S) % D;
@@ -668,8 +774,8 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
                                 int max_block_samples, jsdr_bpsk **out)
 {
     JSDR_REQUIRE(ctx && out && tuning_hz, JSDR_EINVAL, "null argument");
-    JSDR_REQUIRE(rate >= 9600 && nchan > 0 && max_block_samples > 0, JSDR_EINVAL,
-                 "need rate >= 9600, nchan > 0, max_block_samples > 0");
+    JSDR_REQUIRE(rate >= 9600 && rate <= 64 * 9600 && nchan > 0 && nchan <= 65535 && max_block_samples > 0,
+                 JSDR_EINVAL, "need 9600 <= rate <= 614400, 0 < nchan < 65536, max_block_samples > 0");
     JSDR_TRY(ctx->bind());
     jsdr_bpsk *b = new jsdr_bpsk();
     b->ctx = ctx;
@@ -678,7 +784,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     b->nchan = nchan;
     b->max_block = max_block_samples;
     b->max_ds = max_block_samples / b->D + 2;
-    b->max_chunks = (max_block_samples + kChunk - 1) / kChunk + 1;
+    b->max_words = (max_block_samples + 31) / 32 + 1;
     b->max_bits = b->max_ds;
     b->h_tuning.assign(tuning_hz, tuning_hz + nchan);
     const size_t nc = (size_t)nchan;
@@ -696,9 +802,17 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_taps, sizeof(double) * kMaxDsTaps);
     ALLOC(b->d_dmtaps, sizeof(double) * kDmTaps);
     ALLOC(b->d_cossin, sizeof(double) * 512);
+    ALLOC(b->d_cossin2, sizeof(double2) * 257);
     ALLOC(b->d_tu_inc, sizeof(double) * nc);
-    ALLOC(b->d_tu_phase, sizeof(double) * nc);
-    ALLOC(b->d_chunk_phase, sizeof(double) * nc * b->max_chunks);
+    ALLOC(b->d_tu_dx, sizeof(unsigned long long) * nc);
+    ALLOC(b->d_tu_phase0, sizeof(double) * nc);
+    b->d_tu_phase = b->d_tu_phase0;
+    for (int i = 0; i < 2; i++) {
+        ALLOC(b->plan[i].ckpt, sizeof(double) * nc * b->max_words);
+        ALLOC(b->plan[i].phase_end, sizeof(double) * nc);
+        cudaEventCreateWithFlags(&b->plan[i].ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b->plan[i].consumed, cudaEventDisableTiming);
+    }
     ALLOC(b->d_ds_hist[0], sizeof(double2) * kMaxDsTaps * nc);
     ALLOC(b->d_ds_hist[1], sizeof(double2) * kMaxDsTaps * nc);
     ALLOC(b->d_ds_out, sizeof(double2) * nc * b->max_ds);
@@ -716,7 +830,18 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     for (int i = 0; i < 27; i++) taps[i] = (double)kDsFilterF[i];
     for (int i = 0; i < kDmTaps; i++) dmt[i] = (double)kDmFilterF[i];
     std::vector<double> inc(nchan);
-    for (int c = 0; c < nchan; c++) inc[c] = 2.0 * M_PI * tuning_hz[c] / (double)rate;   // :196
+    std::vector<unsigned long long> dx(nchan);
+    for (int c = 0; c < nchan; c++) {
+        inc[c] = 2.0 * M_PI * tuning_hz[c] / (double)rate;   // :196
+        dx[c] = index_step_fixed(inc[c]);
+    }
+    std::vector<double> cs2(2 * 257);
+    for (int n = 0; n < 256; n++) {
+        cs2[2 * n] = cossin[n];
+        cs2[2 * n + 1] = cossin[256 + n];
+    }
+    cs2[512] = cs2[513] = 1.0;     // bypass entry: x*1.0 is exact
+    for (int i = 0; i < kMaxDsTaps; i++) b->h_taps[i] = taps[i];
     std::vector<TimingState> ts(nchan);
     memset(ts.data(), 0, sizeof(TimingState) * nc);
     for (int c = 0; c < nchan; c++) ts[c].dmEnergyOut = 1.0;                             // :499
@@ -724,6 +849,8 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     if (rc == JSDR_OK) rc = upload(ctx, b->d_taps, taps.data(), sizeof(double) * kMaxDsTaps);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_dmtaps, dmt.data(), sizeof(double) * kDmTaps);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_inc, inc.data(), sizeof(double) * nc);
+    if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_dx, dx.data(), sizeof(unsigned long long) * nc);
+    if (rc == JSDR_OK) rc = upload(ctx, b->d_cossin2, cs2.data(), sizeof(double) * 2 * 257);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_ts, ts.data(), sizeof(TimingState) * nc);
     if (rc != JSDR_OK) {
         jsdr_bpsk_destroy(b);
@@ -739,11 +866,15 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     b->ctx->bind();
     cudaStreamSynchronize(b->ctx->side);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase, b->d_chunk_phase,
+    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
                     b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix,
                     b->d_bit_roll, b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_out, b->d_ts, b->d_bits,
                     b->d_bit_at, b->d_nbits, b->d_in};
     for (void *p : ptrs) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (b->plan[i].ready) cudaEventDestroy(b->plan[i].ready);
+        if (b->plan[i].consumed) cudaEventDestroy(b->plan[i].consumed);
+    }
     delete b;
     return JSDR_OK;
 }
@@ -759,8 +890,13 @@ extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
 {
     JSDR_REQUIRE(b && chan >= 0 && chan < b->nchan, JSDR_EINVAL, "bad channel");
     JSDR_TRY(b->ctx->bind());
+    // the scout may be running ahead with the old increment: let it finish and drop its plan
+    JSDR_CUDA(cudaStreamSynchronize(b->ctx->side));
+    b->plan[0].valid = b->plan[1].valid = false;
     b->h_tuning[chan] = hz;
     double inc = 2.0 * M_PI * hz / (double)b->rate;       // :188
+    unsigned long long dx = index_step_fixed(inc);
+    JSDR_TRY(upload(b->ctx, b->d_tu_dx + chan, &dx, sizeof(dx)));
     return upload(b->ctx, b->d_tu_inc + chan, &inc, sizeof(double));
 }
 
@@ -771,6 +907,7 @@ extern "C" int jsdr_bpsk_set_ds_filter(jsdr_bpsk *b, const double *taps, int nta
     std::vector<double> t(kMaxDsTaps, 0.0);
     for (int i = 0; i < ntaps; i++) t[i] = taps[i];
     JSDR_TRY(upload(b->ctx, b->d_taps, t.data(), sizeof(double) * kMaxDsTaps));
+    for (int i = 0; i < kMaxDsTaps; i++) b->h_taps[i] = t[i];
     b->ntaps = ntaps;
     return bpsk_reset_ds(b);
 }

@@ -78,9 +78,51 @@ __device__ __forceinline__ void static_for(F &&f)
     }
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+// ---- packed complex arithmetic ---------------------------------------------
+// sm_100a has two-wide FP32 instructions (PTX add/mul/fma .f32x2 -> SASS FADD2 /
+// FMUL2 / FFMA2) whose operands take a half-swap, per-half negation or a scalar
+// broadcast for free.  A complex value is one 64-bit register pair, so a complex
+// add is ONE instruction, a multiply by -i or +i folds into the consumer, and a
+// complex multiply is two.  The FFT is issue-bound, so this is the main lever.
+__device__ __forceinline__ unsigned long long as_u64(float2 a)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return *reinterpret_cast<unsigned long long *>(&a);
+}
+__device__ __forceinline__ float2 as_f2(unsigned long long a)
+{
+    return *reinterpret_cast<float2 *>(&a);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(r);
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b)          // per-half product
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(r);
+}
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c)  // per-half a*b+c
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(as_u64(a)), "l"(as_u64(b)), "l"(as_u64(c)));
+    return as_f2(r);
+}
+__device__ __forceinline__ float2 bcast(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{   // a*b = a.x*(b.x,b.y) + a.y*(-b.y,b.x)
+    return pfma(bcast(a.y), mul_pi(b), pmul(bcast(a.x), b));
 }
 
 // a * exp(-2*pi*i*K/R), K and R compile-time
@@ -89,13 +131,25 @@ __device__ __forceinline__ float2 cmul_w(float2 a)
 {
     constexpr int k = ((K % R) + R) % R;
     if constexpr (k == 0) return a;
-    else if constexpr (4 * k == R) return make_float2(a.y, -a.x);        // * (-i)
+    else if constexpr (4 * k == R) return mul_mi(a);
     else if constexpr (2 * k == R) return make_float2(-a.x, -a.y);
-    else if constexpr (4 * k == 3 * R) return make_float2(-a.y, a.x);    // * (+i)
-    else {
+    else if constexpr (4 * k == 3 * R) return mul_pi(a);
+    else if constexpr (8 * k == R) {              // (1-i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return pmul(bcast(h), cadd(a, mul_mi(a)));
+    } else if constexpr (8 * k == 3 * R) {        // (-1-i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return pmul(bcast(-h), csub(a, mul_mi(a)));
+    } else if constexpr (8 * k == 5 * R) {        // (-1+i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return pmul(bcast(-h), cadd(a, mul_mi(a)));
+    } else if constexpr (8 * k == 7 * R) {        // (1+i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return pmul(bcast(h), csub(a, mul_mi(a)));
+    } else {
         constexpr float c = (float)cx_cos2pi(k, R);
-        constexpr float s = (float)(-cx_sin2pi(k, R));
-        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+        constexpr float sn = (float)(-cx_sin2pi(k, R));   // w = (c, sn)
+        return pfma(bcast(a.y), make_float2(-sn, c), pmul(bcast(a.x), make_float2(c, sn)));
     }
 }
 
@@ -123,8 +177,8 @@ struct Dft<2, true> {
     static __device__ __forceinline__ void run(float2 *v)
     {
         float2 a = v[0], b = v[1];
-        v[0] = make_float2(a.x + b.x, a.y + b.y);
-        v[1] = make_float2(a.x - b.x, a.y - b.y);
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
     }
 };
 
@@ -132,14 +186,14 @@ template <>
 struct Dft<4, true> {
     static __device__ __forceinline__ void run(float2 *v)
     {
-        float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-        float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-        float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-        float2 a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-        v[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-        v[1] = make_float2(a1.x + a3.y, a1.y - a3.x);   // a1 - i*a3
-        v[2] = make_float2(a0.x - a2.x, a0.y - a2.y);
-        v[3] = make_float2(a1.x - a3.y, a1.y + a3.x);   // a1 + i*a3
+        float2 a0 = cadd(v[0], v[2]);
+        float2 a1 = csub(v[0], v[2]);
+        float2 a2 = cadd(v[1], v[3]);
+        float2 a3 = mul_mi(csub(v[1], v[3]));   // -i*(v1 - v3), folded into the consumers
+        v[0] = cadd(a0, a2);
+        v[1] = cadd(a1, a3);
+        v[2] = csub(a0, a2);
+        v[3] = csub(a1, a3);
     }
 };
 
@@ -152,13 +206,13 @@ struct Dft<P, true> {
         float2 s[H + 1], d[H + 1];
 #pragma unroll
         for (int n = 1; n <= H; n++) {
-            s[n] = make_float2(v[n].x + v[P - n].x, v[n].y + v[P - n].y);
-            d[n] = make_float2(v[n].x - v[P - n].x, v[n].y - v[P - n].y);
+            s[n] = cadd(v[n], v[P - n]);
+            d[n] = csub(v[n], v[P - n]);
         }
         float2 x0 = v[0];
         float2 acc = x0;
 #pragma unroll
-        for (int n = 1; n <= H; n++) { acc.x += s[n].x; acc.y += s[n].y; }
+        for (int n = 1; n <= H; n++) acc = cadd(acc, s[n]);
         v[0] = acc;
         static_for<1, H + 1>([&](auto kk) {
             constexpr int k = decltype(kk)::value;
@@ -167,14 +221,13 @@ struct Dft<P, true> {
                 constexpr int n = decltype(nn)::value;
                 constexpr float c = (float)cx_cos2pi(n * k, P);
                 constexpr float sn = (float)cx_sin2pi(n * k, P);
-                re.x = fmaf(s[n].x, c, re.x);
-                re.y = fmaf(s[n].y, c, re.y);
-                im.x = fmaf(d[n].x, sn, im.x);
-                im.y = fmaf(d[n].y, sn, im.y);
+                re = pfma(s[n], bcast(c), re);
+                if constexpr (n == 1) im = pmul(d[n], bcast(sn));
+                else im = pfma(d[n], bcast(sn), im);
             });
             // X[k] = re - i*im ; X[P-k] = re + i*im
-            v[k] = make_float2(re.x + im.y, re.y - im.x);
-            v[P - k] = make_float2(re.x - im.y, re.y + im.x);
+            v[k] = cadd(re, mul_mi(im));
+            v[P - k] = csub(re, mul_mi(im));
         });
     }
 };
@@ -252,10 +305,18 @@ struct Args {
 };
 
 __device__ __forceinline__ unsigned ordered_key(float v)
-{   // monotone float -> uint; 0 means "not a candidate" (NaN, -inf, <= -FLT_MAX)
-    if (!(v > -3.4028234663852886e38f)) return 0u;
+{   // monotone float -> uint (never 0 for a finite or +inf v); -0.0 counts as +0.0
     unsigned u = __float_as_uint(v + 0.0f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// MUFU.LG2 without the denormal pre-scaling of __log2f: power below 1.2e-38
+// (-379 dB) reads as -inf, exactly as an all-zero bin does.
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <class P, int IN>
@@ -267,9 +328,15 @@ __device__ __forceinline__ float2 load_sample(const Args &a, long blk, int n)
         uint32_t w = ldg_stream_u32(reinterpret_cast<const uint32_t *>(a.in) + blk * P::N + n);
         // JavaAudio.java:281-288: s += (short)ic with 16-bit wrap, then (float)s.
         // The 1/32767 scale is folded into cf (the transform is linear).
-        short si = (short)((int)(w & 0xffffu) + a.ic);
-        short sq = (short)((int)(w >> 16) + a.qc);
-        return make_float2((float)si, (float)sq);
+        if (a.ic | a.qc) {   // uniform branch: the correction is normally zero
+            w = (((w & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((w >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
+        }
+        // exact s16 -> float without the conversion pipe: bias to unsigned, splice into
+        // the mantissa of 2^23, subtract 2^23 + 32768
+        w ^= 0x80008000u;
+        float fi = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)) - 8421376.0f;
+        float fq = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)) - 8421376.0f;
+        return make_float2(fi, fq);
     }
 }
 
@@ -362,7 +429,9 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
     // ---------------- last pass + epilogue
     {
         constexpr int RL = P::RL, ML = P::ML;
-        unsigned best_key = 0u;
+        // running first-strict-maximum exactly as fft.java:201-211: m starts at
+        // -Float.MAX_VALUE, a bin wins only if m < psd (NaN and -inf never do)
+        float best = -3.4028234663852886e38f;
         int best_idx = 0x7fffffff;
         int my_g = 0;
         for (int U = tid; U < P::G * ML; U += P::T) {
@@ -383,21 +452,28 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
                 for (int q = 0; q < RL; q++) stg_stream_f2(spec + j + q * ML, v[q]);
             } else {
                 float *psd = a.out + blk * (long)(N + 2);
+                float it_best = -3.4028234663852886e38f;
+                int it_idx = 0x7fffffff;
 #pragma unroll
                 for (int q = 0; q < RL; q++) {
                     // fft.java:207 in float: (re*re + im*im) * cf, each step rounded
                     float pw = __fmul_rn(__fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y)), a.cf);
-                    float db = 10.0f * log10f(pw);
+                    // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is accurate to ~1e-7 in log2
+                    float db = 3.0102999566398120f * lg2_approx(pw);
                     int k = j + q * ML;
                     stg_stream_f32(psd + k, db);
-                    unsigned key = ordered_key(db);
-                    if (key > best_key || (key == best_key && key != 0u && k < best_idx)) {
-                        best_key = key;
-                        best_idx = k;
+                    if (it_best < db) {            // bins visited in increasing k: first maximum wins
+                        it_best = db;
+                        it_idx = k;
                     }
+                }
+                if (best < it_best || (best == it_best && it_idx < best_idx)) {
+                    best = it_best;
+                    best_idx = it_idx;
                 }
             }
         }
+        const unsigned best_key = (best_idx == 0x7fffffff) ? 0u : ordered_key(best);
         if constexpr (OUT == OUT_PSD) {
             // first strict maximum (fft.java:208-211): max value, lowest bin among equals
             constexpr bool WARP_UNIFORM = (P::G == 1) || (ML % 32 == 0);

@@ -32,7 +32,6 @@ struct TimingState {
     long long cntBit;
 };
 
-constexpr int kChunk = 32;           // samples between tuner phase checkpoints
 constexpr int kMaxDsTaps = 128;
 constexpr int kDmTaps = 65;          // MATCHED_FILTER_SIZE
 
@@ -43,16 +42,30 @@ struct jsdr_bpsk {
     jsdr_ctx *ctx = nullptr;
     int rate = 0, D = 0, nchan = 0, max_block = 0, stages = 3;
     int ntaps = 27;
-    int max_ds = 0, max_chunks = 0, max_bits = 0;
+    int max_ds = 0, max_words = 0, max_bits = 0;
     std::vector<double> h_tuning;
 
     double *d_taps = nullptr;        // [kMaxDsTaps] decimator low-pass
     double *d_dmtaps = nullptr;      // [65] matched filter
     double *d_cossin = nullptr;      // cosTab[256] then sinTab[256]
+    double2 *d_cossin2 = nullptr;    // (cos, sin) pairs, plus entry 256 = (1, 1) for the mixer bypass
 
     double *d_tu_inc = nullptr;      // [nchan] tuPhaseInc
-    double *d_tu_phase = nullptr;    // [nchan] tuPhase (carried)
-    double *d_chunk_phase = nullptr; // [max_chunks][nchan] phase before each chunk
+    unsigned long long *d_tu_dx = nullptr;   // [nchan] table-index step per sample, 8.48 fixed point
+    double *d_tu_phase0 = nullptr;   // [nchan] initial tuPhase (zeros)
+    const double *d_tu_phase = nullptr;   // committed tuPhase: phase0 or the phase_end of the last plan used
+    // Scout output ("plan") for one block.  Two of them: while the data kernels work
+    // through block k, the scout already replays block k+1 on the side stream.
+    struct TunerPlan {
+        double *ckpt = nullptr;      // [max_words][nchan] tuPhase before each 32-sample chunk
+        double *phase_end = nullptr; // [nchan] tuPhase after the block
+        int S = 0;
+        bool valid = false;          // holds the plan for the next S samples from d_tu_phase
+        bool used = false;           // `consumed` has been recorded at least once
+        cudaEvent_t ready = nullptr, consumed = nullptr;
+    } plan[2];
+    int plan_cur = 0;
+    double h_taps[128] = {0};        // host copy of the decimator taps (kernel parameter)
     double2 *d_ds_hist[2] = {nullptr, nullptr};   // [nchan][kMaxDsTaps] last ntaps-1 mixed samples
     int ds_hist_cur = 0;
     int ds_cnt = 0;                  // dsCnt carry (identical for all channels)

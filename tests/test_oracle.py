@@ -218,3 +218,32 @@ def test_bpsk_decimator_impulse_response_is_taps():
     r = b.receive(x)
     got = r["ds"][:3, 0] / (0.9 * 32768.0)
     assert np.allclose(got, [ds[0], ds[10], ds[20]], rtol=1e-15)
+
+
+def test_s16_division_shortcut_is_exact_for_every_input():
+    """The CUDA ingest computes (float)s/32767f as q0 = s*r, e = fma(-q0, 32767, s),
+    q = fma(r, e, q0) with r = fl(1/32767) (csrc/bpsk.cu s16_over_32767).  It must equal
+    the IEEE division of JavaAudio.java:283 for all 65536 inputs (exact rational check)."""
+    from fractions import Fraction
+    f32 = np.float32
+
+    def rnd32(fr):
+        if fr == 0:
+            return f32(0)
+        c = f32(float(fr))
+        best = None
+        for cand in (np.nextafter(c, f32(-np.inf)), c, np.nextafter(c, f32(np.inf))):
+            err = abs(Fraction(float(cand)) - fr)
+            if best is None or err < best[0] or (err == best[0] and (int(cand.view(np.uint32)) & 1) == 0):
+                best = (err, cand)
+        return best[1]
+
+    r = f32(3.0518509447574615e-05)
+    assert r == f32(1.0) / f32(32767.0)
+    fr_r = Fraction(float(r))
+    for x in range(-32768, 32768):
+        xf = Fraction(x)
+        q0 = rnd32(xf * fr_r)
+        e = rnd32(xf - Fraction(float(q0)) * 32767)
+        q = rnd32(Fraction(float(q0)) + fr_r * Fraction(float(e)))
+        assert q == f32(x) / f32(32767.0), x
