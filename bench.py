@@ -45,8 +45,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=4096, help="independent streams per GPU")
-    ap.add_argument("--fft-n", type=int, default=16384, help="block length (complex samples)")
-    ap.add_argument("--blocks", type=int, default=32, help="blocks per channel per step")
+    ap.add_argument("--fft-n", type=int, default=4096, help="block length (complex samples)")
+    ap.add_argument("--blocks", type=int, default=128, help="blocks per channel per step")
     ap.add_argument("--taps", type=int, default=64, help="decimator taps (config 4: 64)")
     ap.add_argument("--e2e-channels", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -1,0 +1,99 @@
+// JsdrCuda.java — java.lang.foreign (FFM, Java 22+) binding of libjsdrcuda.so.
+//
+// NOT COMPILED IN THIS REPOSITORY'S BUILD ENVIRONMENT: the image has no JDK (see
+// DESIGN.md).  It is the reference-side binding a java-sdr maintainer adds next to
+// fft.java / FUNcubeBPSKDemod.java; every downcall below is one entry point of
+// include/jsdrcuda.h, with the same argument order.  The Python mirror of these
+// classes (java-sdr_b200/jsdrcuda) is what the tests drive through the same ABI.
+package com.ashbysoft.java_sdr;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+public final class JsdrCuda {
+	public static final int MEM_HOST = 0, MEM_DEVICE = 1;
+
+	private static final Linker LINKER = Linker.nativeLinker();
+	private static final SymbolLookup LIB = SymbolLookup.libraryLookup(
+		System.getProperty("jsdrcuda.lib", "libjsdrcuda.so"), Arena.global());
+
+	private static MethodHandle h(String name, FunctionDescriptor fd) {
+		return LINKER.downcallHandle(LIB.find(name).orElseThrow(
+			() -> new UnsatisfiedLinkError("libjsdrcuda.so lacks " + name)), fd);
+	}
+
+	static final MethodHandle LAST_ERROR = h("jsdr_last_error", FunctionDescriptor.of(ADDRESS));
+	static final MethodHandle CTX_CREATE = h("jsdr_ctx_create", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS));
+	static final MethodHandle CTX_DESTROY = h("jsdr_ctx_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+	static final MethodHandle HOST_ALLOC = h("jsdr_host_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
+	static final MethodHandle HOST_FREE = h("jsdr_host_free", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	// fft.java
+	static final MethodHandle FFT_CREATE = h("jsdr_fft_create",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+	static final MethodHandle FFT_DESTROY = h("jsdr_fft_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+	static final MethodHandle FFT_RECEIVE_F32 = h("jsdr_fft_receive_f32",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle FFT_RECEIVE_S16 = h("jsdr_fft_receive_s16",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	// FUNcubeBPSKDemod.java
+	static final MethodHandle BPSK_CREATE = h("jsdr_bpsk_create",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+	static final MethodHandle BPSK_DESTROY = h("jsdr_bpsk_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+	static final MethodHandle BPSK_SET_TUNING = h("jsdr_bpsk_set_tuning",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE));
+	static final MethodHandle BPSK_RECEIVE_F32 = h("jsdr_bpsk_receive_f32",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT));
+	static final MethodHandle BPSK_RECEIVE_S16 = h("jsdr_bpsk_receive_s16",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_INT));
+	static final MethodHandle BPSK_READ_BITS = h("jsdr_bpsk_read_bits",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+	static final MethodHandle BPSK_READ_COUNTERS = h("jsdr_bpsk_read_counters",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+
+	/** Status code to message; never throws out of a handler (JavaAudio.java:321-323). */
+	static String check(int rc) {
+		if (rc == 0) return null;
+		try {
+			MemorySegment s = (MemorySegment) LAST_ERROR.invokeExact();
+			return "jsdrcuda " + rc + ": " + s.reinterpret(512).getString(0);
+		} catch (Throwable t) {
+			return "jsdrcuda " + rc;
+		}
+	}
+
+	/** One context per JVM / GPU; pinned rings are allocated from it. */
+	public static final class Context implements AutoCloseable {
+		final MemorySegment handle;
+		final Arena arena = Arena.ofShared();
+
+		public Context(int device) throws Throwable {
+			MemorySegment out = arena.allocate(ADDRESS);
+			String err = check((int) CTX_CREATE.invokeExact(device, out));
+			if (err != null) throw new IllegalStateException(err);   // no CPU fallback by design
+			handle = out.get(ADDRESS, 0);
+		}
+
+		/** Pinned host memory the audio thread fills and the GPU reads by DMA. */
+		public MemorySegment pinned(long bytes) throws Throwable {
+			MemorySegment out = arena.allocate(ADDRESS);
+			String err = check((int) HOST_ALLOC.invokeExact(handle, bytes, out));
+			if (err != null) throw new OutOfMemoryError(err);
+			return out.get(ADDRESS, 0).reinterpret(bytes);
+		}
+
+		@Override
+		public void close() {
+			try { int rc = (int) CTX_DESTROY.invokeExact(handle); } catch (Throwable t) { }
+			arena.close();
+		}
+	}
+}
