@@ -64,6 +64,15 @@ int         jsdr_ctx_sync(jsdr_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int         jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count);
 
+/* Optional per-kernel timing: while enabled, every launch of the kernels below is
+ * bracketed by CUDA events on its own stream; _read waits for the work and returns
+ * the summed milliseconds and launch counts per kind since the last read
+ * (ms/count hold JSDR_K_COUNT entries).  bench.py's roofline numbers come from here. */
+enum { JSDR_K_FFT = 0, JSDR_K_MIXDECIM = 1, JSDR_K_MATCHED = 2, JSDR_K_TIMING = 3, JSDR_K_SCOUT = 4,
+       JSDR_K_OTHER = 5, JSDR_K_COUNT = 6 };
+int         jsdr_ctx_profile(jsdr_ctx *ctx, int enable);
+int         jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, int nkinds);
+
 /* pinned host rings handed to Java as MemorySegments; plain device buffers for
  * device-resident batches */
 int jsdr_host_alloc(jsdr_ctx *ctx, size_t bytes, void **out);
@@ -120,6 +129,19 @@ int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double *tuning_hz
 int jsdr_bpsk_destroy(jsdr_bpsk *b);
 int jsdr_bpsk_set_stages(jsdr_bpsk *b, int stages);
 int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz);       /* :174-189 */
+/* Arithmetic of the tuner + decimator stage.  JSDR_PREC_F64 (default) is the
+ * reference's binary64 in the reference's operation order: every output is
+ * bit-identical to the Java arithmetic, and the bits that follow are exact.
+ * JSDR_PREC_F32 keeps the exact tuner table index sequence but mixes and filters
+ * in binary32 (filtered samples within 1e-4 of full scale of the binary64 path);
+ * it is meant for channeliser use (stages == 1), not for bit decisions. */
+enum { JSDR_PREC_F64 = 0, JSDR_PREC_F32 = 1 };
+int jsdr_bpsk_set_precision(jsdr_bpsk *b, int precision);
+/* Kernel choice for the tuner + decimator (results are identical): AUTO picks the
+ * streaming kernel (one lane per channel) for banks of >= 32 channels of s16 input
+ * and the tile kernel (one CTA per channel tile) otherwise. */
+enum { JSDR_KERNEL_AUTO = 0, JSDR_KERNEL_TILE = 1, JSDR_KERNEL_STREAM = 2 };
+int jsdr_bpsk_set_kernel(jsdr_bpsk *b, int mode);
 /* replace the 27-tap decimator low-pass (BASELINE config 4 uses 64 taps); resets
  * the decimator history like a fresh instance */
 int jsdr_bpsk_set_ds_filter(jsdr_bpsk *b, const double *taps, int ntaps);

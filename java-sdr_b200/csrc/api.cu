@@ -56,7 +56,13 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    {   // the side stream carries the serial, data-independent phase replay: highest priority, so
+        // that its few small CTAs are placed as soon as a slot frees up instead of queueing behind
+        // the whole grid of the data kernel that runs beside it
+        int lo = 0, hi = 0;
+        JSDR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi));
+    }
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t0));
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t1));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -75,6 +81,11 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
     cudaEventDestroy(ctx->ev_t1);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
+    for (auto *v : {&ctx->spans, &ctx->free_spans})
+        for (jsdr_prof_span &sp : *v) {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->side);
     delete ctx;
@@ -94,6 +105,35 @@ extern "C" int jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count)
 {
     JSDR_REQUIRE(ctx && count, JSDR_EINVAL, "null argument");
     *count = ctx->launches;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_ctx_profile(jsdr_ctx *ctx, int enable)
+{
+    JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    ctx->profiling = enable != 0;
+    return JSDR_OK;
+}
+
+// Sum the event-bracketed durations recorded since the last read, per kernel kind.
+extern "C" int jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, int nkinds)
+{
+    JSDR_REQUIRE(ctx && ms && count && nkinds >= JSDR_K_COUNT, JSDR_EINVAL, "need room for JSDR_K_COUNT kinds");
+    JSDR_TRY(ctx->bind());
+    JSDR_CUDA(cudaStreamSynchronize(ctx->side));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < nkinds; k++) {
+        ms[k] = 0.0;
+        count[k] = 0;
+    }
+    for (jsdr_prof_span &sp : ctx->spans) {
+        float t = 0.f;
+        JSDR_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.kind] += t;
+        count[sp.kind]++;
+        ctx->free_spans.push_back(sp);
+    }
+    ctx->spans.clear();
     return JSDR_OK;
 }
 

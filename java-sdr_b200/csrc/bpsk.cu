@@ -17,6 +17,8 @@
 //   * only the bit-timing tracker (:533-595) is data-dependent; it runs one
 //     thread per channel over the 9600 S/s stream.
 #include <math.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include <vector>
@@ -127,6 +129,23 @@ __device__ __forceinline__ void raw_to_iq(typename RawT<FMT>::type w, int ic, in
 // (the phase before the first sample) for every 32-sample chunk.  It runs on the
 // side stream, one block ahead of the data (see bpsk_receive), and costs almost no
 // issue slots, so it hides behind the data kernels.
+// Two reference steps in three dependent additions.  With 0 < inc < pi a wrap cannot follow a
+// wrap, so the pair is one of (no wrap, no wrap), (wrap, none), (none, wrap); which one is read
+// off the phase BEFORE the pair (p > 2pi-inc, p > 2pi-2inc), off the critical path, and the
+// additions are the reference's own: t1 = p+inc; t2 = t1 + (-2pi | inc); t3 = t2 + (inc | -2pi | 0).
+// The prediction compares against rounded thresholds; when p is within 2^-40 of one of them the
+// 32-sample chunk is replayed step by step instead (checked once per chunk, off the chain).
+__device__ __forceinline__ double phase_step2(double p, double inc, double th1, double th2, bool &risky)
+{
+    const bool m1 = p > th1, m2 = p > th2;
+    risky |= (fabs(__dadd_rn(p, -th1)) < 9.094947017729282e-13) | (fabs(__dadd_rn(p, -th2)) < 9.094947017729282e-13);
+    const double s2 = m1 ? -kTwoPi : inc;
+    const double s3 = m1 ? inc : (m2 ? -kTwoPi : 0.0);
+    const double t1 = __dadd_rn(p, inc);
+    const double t2 = __dadd_rn(t1, s2);
+    return __dadd_rn(t2, s3);
+}
+
 __global__ void __launch_bounds__(32)
 k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_in,
               double *__restrict__ phase_out, double *__restrict__ ckpt, int nchan, int S)
@@ -136,10 +155,25 @@ k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_
     double p = phase_in[ch];
     const double inc = inc_[ch];
     const int nfull = S >> 5;
-    for (int w = 0; w < nfull; w++) {
-        ckpt[(size_t)w * nchan + ch] = p;
+    if (inc > 0.0 && inc < 3.1 && p >= 0.0 && p <= kTwoPi) {
+        const double th1 = __dadd_rn(kTwoPi, -inc), th2 = __dadd_rn(th1, -inc);
+        for (int w = 0; w < nfull; w++) {
+            ckpt[(size_t)w * nchan + ch] = p;
+            const double p0 = p;
+            bool risky = false;
 #pragma unroll
-        for (int j = 0; j < 32; j++) p = phase_step(p, inc);
+            for (int j = 0; j < 16; j++) p = phase_step2(p, inc, th1, th2, risky);
+            if (risky) {
+                p = p0;
+                for (int j = 0; j < 32; j++) p = phase_step(p, inc);
+            }
+        }
+    } else {                                           // increments the pair form does not cover
+        for (int w = 0; w < nfull; w++) {
+            ckpt[(size_t)w * nchan + ch] = p;
+#pragma unroll 4
+            for (int j = 0; j < 32; j++) p = phase_step(p, inc);
+        }
     }
     if (S & 31) {
         ckpt[(size_t)nfull * nchan + ch] = p;
@@ -376,6 +410,12 @@ __global__ void k_tuner_tail(const MixParams p)
     p.hist_out[(size_t)ch * kMaxDsTaps + k] = v;
 }
 
+}  // namespace bpsk
+}  // namespace jsdr
+#include "bpsk_stream.cuh"
+namespace jsdr {
+namespace bpsk {
+
 // ------------------------------------------------------------------ matched filter
 struct DmParams {
     const double2 *ds;         // [nchan][max_ds]
@@ -547,11 +587,23 @@ unsigned long long index_step_fixed(double inc)
     return v ? v : 1ull;
 }
 
+// The same step in 8.56 fixed point for the streaming kernel.  0 selects exact replay:
+// increments that are not positive and below pi (two wraps in a row, mixer bypass).
+unsigned long long index_step_fixed56(double inc)
+{
+    if (!(inc > 0.0) || !(inc < 3.1)) return 0ull;
+    const long double c = 256.0L / (long double)(2.0 * M_PI);
+    long double d = fmodl((long double)inc * c, 256.0L);
+    unsigned long long v = (unsigned long long)(d * 72057594037927936.0L + 0.5L);
+    return v ? v : 1ull;
+}
+
 // Replay the tuner phase over the next S samples from the committed phase into `P`
 // (side stream).
 int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
 {
     jsdr_ctx *ctx = b->ctx;
+    ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
     k_tuner_scout<<<(b->nchan + 31) / 32, 32, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
                                                              b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
@@ -597,6 +649,66 @@ int bpsk_reset_ds(jsdr_bpsk *b)
     b->ds_cnt = 0;
     b->ds_hist_cur = 0;
     return JSDR_OK;
+}
+
+// The streaming tuner + decimator: one lane per channel, one warp per segment of R outputs.
+template <int PREC, int NTAPS, int DD>
+int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
+{
+    jsdr_ctx *ctx = b->ctx;
+    constexpr int W = stream::kWarps;
+    auto kern = stream::k_mixdecim_stream<PREC, NTAPS, DD, W>;
+    constexpr size_t smem = stream::smem_bytes<W>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int warps = sp.ncw * sp.nseg;
+    const int grid = std::min((warps + W - 1) / W, ctx->sm_count);   // one CTA per SM, warps loop over segments
+    ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
+    kern<<<grid, W * 32, smem, ctx->stream>>>(sp);
+    return launched(ctx, "k_mixdecim_stream");
+}
+
+int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
+{
+    stream::Params sp;
+    sp.in = reinterpret_cast<const uint32_t *>(mp.in);
+    sp.chan_stride = mp.chan_stride;
+    sp.S = S;
+    sp.ic = mp.ic;
+    sp.qc = mp.qc;
+    sp.tu_dx56 = b->d_tu_dx56;
+    sp.tu_inc = mp.tu_inc;
+    sp.ckpt = mp.ckpt;
+    sp.nchan = mp.nchan;
+    sp.nchunks = (S + 31) / 32;
+    sp.hist_in = mp.hist_in;
+    sp.cossin = mp.cossin;
+    sp.n0 = mp.n0;
+    sp.NO = mp.NO;
+    sp.ncw = (mp.nchan + 31) / 32;
+    // segments: a few per resident warp so that the SMs stay evenly loaded, but long enough
+    // that the NQ-1 warm-up periods of a segment do not matter
+    const int want_warps = b->ctx->sm_count * stream::kWarps * 3;
+    int nseg = (want_warps + sp.ncw - 1) / sp.ncw;
+    int R = (mp.NO + nseg - 1) / nseg;
+    if (R < 64) R = 64;
+    sp.R = R;
+    sp.nseg = (mp.NO + R - 1) / R;
+    sp.ds_out = mp.ds_out;
+    sp.max_ds = mp.max_ds;
+    for (int k = 0; k < stream::kMaxTaps; k++) {
+        sp.taps[k] = (k < b->ntaps) ? b->h_taps[k] : 0.0;
+        sp.tapsf[k] = (float)sp.taps[k];
+    }
+    const bool f32 = b->precision == JSDR_PREC_F32;
+    if (b->ntaps == 27 && mp.D == 10)
+        return f32 ? launch_stream_shape<stream::PREC_F32, 27, 10>(b, sp) : launch_stream_shape<stream::PREC_F64, 27, 10>(b, sp);
+    if (b->ntaps == 27 && mp.D == 20)
+        return f32 ? launch_stream_shape<stream::PREC_F32, 27, 20>(b, sp) : launch_stream_shape<stream::PREC_F64, 27, 20>(b, sp);
+    return f32 ? launch_stream_shape<stream::PREC_F32, 64, 20>(b, sp) : launch_stream_shape<stream::PREC_F64, 64, 20>(b, sp);
 }
 
 // `after_input` (optional) is called once the input is on the device and before
@@ -688,7 +800,18 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
             mp.off[k] = (int)sizeof(double2) * (d + mp.pad * (d / D));
         }
     }
-    if (NO > 0) {
+    bool streamed = false;
+    if (NO > 0 && FMT == FMT_S16 && b->kernel_mode != JSDR_KERNEL_TILE) {
+        // many channels: the streaming kernel (bpsk_stream.cuh); needs a compiled (taps, D) shape
+        const bool shape_ok = (b->ntaps == 27 && D == 10) || (b->ntaps == 27 && D == 20) || (b->ntaps == 64 && D == 20);
+        const bool want = b->kernel_mode == JSDR_KERNEL_STREAM || (nchan >= 32 && NO >= 64) ||
+                          (b->precision == JSDR_PREC_F32 && nchan >= 8);
+        if (shape_ok && want) {
+            JSDR_TRY(launch_stream(b, mp, P.S));
+            streamed = true;
+        }
+    }
+    if (NO > 0 && !streamed) {
         const int span = (kTileOut - 1) * D + b->ntaps;
         const size_t m_bytes = sizeof(double2) * (size_t)(span + mp.pad * (span / D) + 2);
         mp.ix_off = (int)m_bytes;
@@ -700,6 +823,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         else if (b->ntaps == 27 && D == 20) kern = k_mixdecim<FMT, 27, 20>;
         else if (b->ntaps == 64 && D == 20) kern = k_mixdecim<FMT, 64, 20>;
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
         kern<<<grid, kTileThreads, smem, ctx->stream>>>(mp);
         JSDR_TRY(launched(ctx, "k_mixdecim"));
     }
@@ -739,7 +863,10 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         dp.base65 = (int)(b->cnt_ds % 65);
         dp.dm_out = b->d_dm_out;
         dim3 grid((NO + kDmTile - 1) / kDmTile, nchan);
-        k_matched<<<grid, 2 * kDmTile, 0, ctx->stream>>>(dp);
+        {
+            ProfScope prof(ctx, JSDR_K_MATCHED, ctx->stream);
+            k_matched<<<grid, 2 * kDmTile, 0, ctx->stream>>>(dp);
+        }
         JSDR_TRY(launched(ctx, "k_matched"));
         k_dm_tail<<<nchan, 64, 0, ctx->stream>>>(dp);
         JSDR_TRY(launched(ctx, "k_dm_tail"));
@@ -757,6 +884,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
             tp.nbits = b->d_nbits;
             tp.max_bits = b->max_bits;
             tp.cnt_ds0 = b->cnt_ds;
+            ProfScope prof(ctx, JSDR_K_TIMING, ctx->stream);
             k_timing<<<(nchan + 127) / 128, 128, 0, ctx->stream>>>(tp);
             JSDR_TRY(launched(ctx, "k_timing"));
         }
@@ -805,6 +933,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_cossin2, sizeof(double2) * 257);
     ALLOC(b->d_tu_inc, sizeof(double) * nc);
     ALLOC(b->d_tu_dx, sizeof(unsigned long long) * nc);
+    ALLOC(b->d_tu_dx56, sizeof(unsigned long long) * nc);
     ALLOC(b->d_tu_phase0, sizeof(double) * nc);
     b->d_tu_phase = b->d_tu_phase0;
     for (int i = 0; i < 2; i++) {
@@ -830,10 +959,11 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     for (int i = 0; i < 27; i++) taps[i] = (double)kDsFilterF[i];
     for (int i = 0; i < kDmTaps; i++) dmt[i] = (double)kDmFilterF[i];
     std::vector<double> inc(nchan);
-    std::vector<unsigned long long> dx(nchan);
+    std::vector<unsigned long long> dx(nchan), dx56(nchan);
     for (int c = 0; c < nchan; c++) {
         inc[c] = 2.0 * M_PI * tuning_hz[c] / (double)rate;   // :196
         dx[c] = index_step_fixed(inc[c]);
+        dx56[c] = index_step_fixed56(inc[c]);
     }
     std::vector<double> cs2(2 * 257);
     for (int n = 0; n < 256; n++) {
@@ -850,6 +980,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     if (rc == JSDR_OK) rc = upload(ctx, b->d_dmtaps, dmt.data(), sizeof(double) * kDmTaps);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_inc, inc.data(), sizeof(double) * nc);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_dx, dx.data(), sizeof(unsigned long long) * nc);
+    if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_dx56, dx56.data(), sizeof(unsigned long long) * nc);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_cossin2, cs2.data(), sizeof(double) * 2 * 257);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_ts, ts.data(), sizeof(TimingState) * nc);
     if (rc != JSDR_OK) {
@@ -866,7 +997,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     b->ctx->bind();
     cudaStreamSynchronize(b->ctx->side);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
+    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
                     b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix,
                     b->d_bit_roll, b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_out, b->d_ts, b->d_bits,
                     b->d_bit_at, b->d_nbits, b->d_in};
@@ -886,6 +1017,20 @@ extern "C" int jsdr_bpsk_set_stages(jsdr_bpsk *b, int stages)
     return JSDR_OK;
 }
 
+extern "C" int jsdr_bpsk_set_precision(jsdr_bpsk *b, int precision)
+{
+    JSDR_REQUIRE(b && (precision == JSDR_PREC_F64 || precision == JSDR_PREC_F32), JSDR_EINVAL, "bad precision");
+    b->precision = precision;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_bpsk_set_kernel(jsdr_bpsk *b, int mode)
+{
+    JSDR_REQUIRE(b && mode >= JSDR_KERNEL_AUTO && mode <= JSDR_KERNEL_STREAM, JSDR_EINVAL, "bad kernel mode");
+    b->kernel_mode = mode;
+    return JSDR_OK;
+}
+
 extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
 {
     JSDR_REQUIRE(b && chan >= 0 && chan < b->nchan, JSDR_EINVAL, "bad channel");
@@ -897,6 +1042,8 @@ extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
     double inc = 2.0 * M_PI * hz / (double)b->rate;       // :188
     unsigned long long dx = index_step_fixed(inc);
     JSDR_TRY(upload(b->ctx, b->d_tu_dx + chan, &dx, sizeof(dx)));
+    unsigned long long dx56 = index_step_fixed56(inc);
+    JSDR_TRY(upload(b->ctx, b->d_tu_dx56 + chan, &dx56, sizeof(dx56)));
     return upload(b->ctx, b->d_tu_inc + chan, &inc, sizeof(double));
 }
 

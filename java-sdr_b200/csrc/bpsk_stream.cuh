@@ -1,0 +1,375 @@
+// bpsk_stream.cuh — the streaming form of the FUNcube tuner + decimator
+// (FUNcubeBPSKDemod.java:382-397 RxMixTuner, :467-492 RxDownSample) for banks of
+// many channels.  Included by bpsk.cu (uses its phase / conversion helpers).
+//
+// Mapping: one LANE per channel, one WARP per (32 consecutive channels, segment of
+// R decimated outputs).  Every lane walks its own channel backwards in time, one
+// "period" of D input samples at a time.  A sample is converted and mixed ONCE, in
+// registers, and feeds the ceil(NTAPS/D) outputs whose windows contain it ("roles":
+// role q of period t is output t-q of the segment and uses taps q*D .. q*D+D-1).
+// Walking newest -> oldest makes every output accumulate its taps in the order
+// k = 0, 1, .. exactly as RxDownSample does (:479-483), so the binary64 variant is
+// bit-identical to the Java arithmetic; at the end of a period the oldest role is
+// complete, is scaled (:486) and stored, and the roles rotate.
+//
+// Memory: raw s16 IQ goes HBM -> registers -> shared memory as whole, aligned
+// 128-byte row chunks (32 samples; 8 lanes x 16 B per row, 4 rows per warp
+// instruction), one chunk ahead of the arithmetic, into a 64-sample ring per row;
+// each lane then reads its own row (odd pitch, no bank conflicts).  Nothing but the decimated output is written back: 4 B in and 16/D B
+// out per input sample.  The cos/sin table sits in shared memory in 8 (binary64) or
+// 16 (binary32) interleaved copies so that the per-lane lookups never conflict.
+//
+// Tuner phase: the table index of sample s is the integer part of
+// x = tuPhase*256/2pi.  x is carried in 8.56 fixed point, anchored at the scout's
+// exact checkpoint (bpsk.cu) and stepped by integer adds.  The reference's rounding
+// can move the true value by < 2^-39 over the <= 64 steps from an anchor, so the
+// integer part is the reference's index unless x is within 2^-24 of an integer; such
+// samples (about one in 2^23), and channels whose increment has no fixed-point form,
+// are resolved by replaying the reference's own double arithmetic from the checkpoint.
+#pragma once
+
+namespace jsdr {
+namespace bpsk {
+namespace stream {
+
+constexpr int kWarps = 15;
+constexpr int kMaxTaps = 64;
+enum { PREC_F64 = 0, PREC_F32 = 1 };
+
+struct Params {
+    const uint32_t *in;                 // [nchan][chan_stride] s16 IQ pairs
+    long long chan_stride;
+    int S, ic, qc;
+    const unsigned long long *tu_dx56;  // [nchan] index step per sample, 8.56 fixed point; 0: exact replay only
+    const double *tu_inc;               // [nchan]
+    const double *ckpt;                 // [nchunks][nchan] tuPhase before each 32-sample chunk
+    int nchan, nchunks;
+    const double2 *hist_in;             // [nchan][kMaxDsTaps], entry k is local sample k-H
+    const double2 *cossin;              // [257] (cos, sin); entry 256 = (1, 1), the mixer bypass
+    int n0, NO, R, nseg, ncw;           // first output's sample, outputs, outputs per segment, segments, channel groups
+    double2 *ds_out;
+    int max_ds;
+    double taps[kMaxTaps];
+    float tapsf[kMaxTaps];
+};
+
+__device__ __forceinline__ unsigned long long u64_of(float2 a) { return *reinterpret_cast<unsigned long long *>(&a); }
+__device__ __forceinline__ float2 f2_of(unsigned long long a) { return *reinterpret_cast<float2 *>(&a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{   // per-half a*b+c in one FFMA2
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(u64_of(a)), "l"(u64_of(b)), "l"(u64_of(c)));
+    return f2_of(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64_of(a)), "l"(u64_of(b)));
+    return f2_of(r);
+}
+
+// tuPhase -> x = tuPhase*256/2pi in 8.56 fixed point (mod 256), to within 2^-47
+__device__ __forceinline__ unsigned long long phase_to_x56(double ph)
+{
+    const double hi = __dmul_rn(ph, kIdxScaleHi);
+    const double lo = __fma_rn(ph, kIdxScaleLo, __fma_rn(ph, kIdxScaleHi, -hi));
+    const unsigned long long x48 = (unsigned long long)(__double2ll_rn(hi * 281474976710656.0) +
+                                                        __double2ll_rn(lo * 281474976710656.0));
+    return x48 << 8;
+}
+
+// The reference's own arithmetic for the D samples s_hi, s_hi-1, .. of one lane:
+// replay tuPhase from the checkpoint and leave the table index of sample s_hi-j in
+// out[j] (256 = mixer bypass).
+__device__ __noinline__ void exact_period_indices(const double *__restrict__ ckpt, double inc, int nchan, int S, int ch,
+                                                  int s_hi, int D, uint16_t *out)
+{
+    for (int j = 0; j < D; j++) out[j] = 0;
+    const int s_lo = max(s_hi - D + 1, 0), s_top = min(s_hi, S - 1);
+    if (s_top < s_lo) return;
+    const int c = s_lo >> 5;
+    double ph = ckpt[(size_t)c * nchan + ch];
+    for (int s = c << 5; s <= s_top; s++) {
+        ph = phase_step(ph, inc);
+        if (s >= s_lo) out[s_hi - s] = (uint16_t)tuner_index(ph);
+    }
+}
+
+template <int PREC>
+struct Acc;
+template <>
+struct Acc<PREC_F64> {
+    double i, q;
+    __device__ __forceinline__ void zero() { i = 0.0; q = 0.0; }
+};
+template <>
+struct Acc<PREC_F32> {
+    float i, q;
+    __device__ __forceinline__ void zero() { i = 0.f; q = 0.f; }
+};
+
+constexpr int kRing = 64;                 // samples per row in the ring: two 32-sample chunks
+constexpr int kPitch = kRing + 1;         // odd pitch (words): row-per-lane reads never conflict
+constexpr int kScratch = 24;              // uint16 per lane for the exact-replay path (>= D)
+constexpr int kTabBytes = 257 * 128;      // 8 x double2 or 16 x float2 copies of each of the 257 entries
+
+template <int W>
+constexpr size_t smem_bytes()
+{
+    return (size_t)kTabBytes + (size_t)W * (32 * kPitch * 4 + 32 * kScratch * 2);
+}
+
+__device__ __forceinline__ double2 lds_d2(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(unsigned addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+// One period (D samples, newest first) of one lane: table lookups, mix, and the
+// multiply-accumulates of the NQ live outputs.  FAST = every sample of the period
+// is a sample of this call (not history), the period does not wrap in the ring and
+// there is no I/Q correction, so the reads are at fixed offsets below `top`;
+// otherwise each sample checks for itself.
+template <int PREC, int NTAPS, int DD, bool FAST>
+__device__ __forceinline__ void period_body(const Params &p, const uint32_t *myrow, const unsigned (&taddr)[DD], int s_hi,
+                                            int ch, Acc<PREC> (&acc)[(NTAPS + DD - 1) / DD])
+{
+    constexpr int NQ = (NTAPS + DD - 1) / DD;
+    constexpr int H = NTAPS - 1;
+    const uint32_t *top = myrow + (s_hi & (kRing - 1));
+#pragma unroll
+    for (int j = 0; j < DD; j++) {
+        const int s = s_hi - j;
+        bool hist = false;
+        uint32_t w = 0;
+        if constexpr (FAST) {
+            w = top[-j];
+        } else {
+            hist = s < 0;
+            if (!hist) {
+                w = myrow[s & (kRing - 1)];
+                w = (((w & 0xffffu) + (unsigned)p.ic) & 0xffffu) | ((((w >> 16) + (unsigned)p.qc) & 0xffffu) << 16);
+            }
+        }
+        w ^= 0x80008000u;              // exact s16 -> float: splice into the mantissa of 2^23
+        const float fi = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)) - 8421376.0f;
+        const float fq = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)) - 8421376.0f;
+        if constexpr (PREC == PREC_F64) {
+            const double xi = (double)s16_over_32767(fi);      // JavaAudio.java:283
+            const double xq = (double)s16_over_32767(fq);
+            const double2 cs = lds_d2(taddr[j]);
+            double mi = __dmul_rn(xi, cs.x);   // :389-390 i*cosTab[ix], q*sinTab[ix]
+            double mq = __dmul_rn(xq, cs.y);
+            if (!FAST && hist) {
+                const int k = s + H;
+                double2 hv = make_double2(0.0, 0.0);
+                if (k >= 0) hv = p.hist_in[(size_t)ch * kMaxDsTaps + k];
+                mi = hv.x;
+                mq = hv.y;
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int k = j + q * DD;
+                if (k < NTAPS) {
+                    acc[q].i = __dadd_rn(acc[q].i, __dmul_rn(mi, p.taps[k]));   // :479-483, age order
+                    acc[q].q = __dadd_rn(acc[q].q, __dmul_rn(mq, p.taps[k]));
+                }
+            }
+        } else {
+            const float2 cs = lds_f2(taddr[j]);
+            float mi = fi * cs.x;
+            float mq = fq * cs.y;
+            if (!FAST && hist) {
+                const int k = s + H;
+                double2 hv = make_double2(0.0, 0.0);
+                if (k >= 0) hv = p.hist_in[(size_t)ch * kMaxDsTaps + k];
+                mi = (float)hv.x;
+                mq = (float)hv.y;
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int k = j + q * DD;
+                if (k < NTAPS) {
+                    acc[q].i = fmaf(mi, p.tapsf[k], acc[q].i);
+                    acc[q].q = fmaf(mq, p.tapsf[k], acc[q].q);
+                }
+            }
+        }
+    }
+}
+
+template <int PREC, int NTAPS, int DD, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
+{
+    constexpr int NQ = (NTAPS + DD - 1) / DD;          // live outputs per sample
+    constexpr int WARP_BYTES = 32 * kPitch * 4 + 32 * kScratch * 2;
+    static_assert(DD <= kScratch && DD <= 32, "period");
+    static_assert(NTAPS <= kMaxTaps && NQ <= 4, "taps");
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- table copies: copy c of entry e at byte e*128 + c*(128/NCOPY)
+    if constexpr (PREC == PREC_F64) {
+        double2 *tab = reinterpret_cast<double2 *>(smem);
+        for (int i = tid; i < 257 * 8; i += W * 32) tab[i] = p.cossin[i >> 3];
+    } else {
+        float2 *tab = reinterpret_cast<float2 *>(smem);
+        for (int i = tid; i < 257 * 16; i += W * 32) {
+            const double2 cs = p.cossin[i >> 4];
+            // the 1/32767 of the s16 conversion (JavaAudio.java:283) folded into the table
+            tab[i] = make_float2((float)(cs.x / 32767.0), (float)(cs.y / 32767.0));
+        }
+    }
+    __syncthreads();
+    // shared-window address of this lane's copy of table entry 0 (128-byte aligned base: the index is or-ed in)
+    const unsigned lane_tab = (unsigned)__cvta_generic_to_shared(smem) + ((PREC == PREC_F64) ? (lane & 7) * 16 : (lane & 15) * 8);
+
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kTabBytes + warp * WARP_BYTES);
+    uint16_t *scratch = reinterpret_cast<uint16_t *>(smem + kTabBytes + warp * WARP_BYTES + 32 * kPitch * 4) + lane * kScratch;
+    const uint32_t *myrow = ring + lane * kPitch;
+
+    // staging role of this lane: rows 4i + (lane>>3), 16-byte piece (lane&7) of a 32-sample chunk
+    const int srow = lane >> 3, spiece = lane & 7;
+    const long long stride4 = 4 * p.chan_stride;       // samples between this lane's consecutive staging rows
+    const bool aligned = ((reinterpret_cast<size_t>(p.in) & 15) == 0) && ((p.chan_stride & 3) == 0);
+    const bool iqcorr = (p.ic | p.qc) != 0;
+
+    for (int wg = blockIdx.x * W + warp; wg < p.ncw * p.nseg; wg += gridDim.x * W) {
+        const int cw = wg % p.ncw, seg = wg / p.ncw;
+        const int ch0 = cw * 32;
+        const int rows = min(32, p.nchan - ch0);
+        const int ch = min(ch0 + lane, p.nchan - 1);
+        const bool lane_live = ch0 + lane < p.nchan;
+        const int m_top = (seg + 1) * p.R - 1;         // newest output of the segment (may lie beyond NO)
+        const int n_top = p.n0 + m_top * DD;           // its newest input sample
+        const int nper = p.R + NQ - 1;
+        const unsigned long long dx = p.tu_dx56[ch];
+        const bool exact_lane = (dx == 0ull);
+        const uint32_t *stage0 = p.in + (long long)(ch0 + srow) * p.chan_stride + spiece * 4;
+
+        // ---- staging: chunk c = samples [32c, 32c+32) of 32 rows -> ring slot c&1
+        uint4 pre[8];
+        auto load_chunk = [&](int c) {
+            const int s0 = c * 32 + spiece * 4;
+            if (c >= 0 && aligned && c * 32 + 32 <= p.S && rows == 32) {
+                const uint32_t *src = stage0 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    pre[i] = ldg_stream_u4(reinterpret_cast<const uint4 *>(src));
+                    src += stride4;
+                }
+            } else {                                   // block edges, short or unaligned rows
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const bool rok = c >= 0 && (srow + 4 * i) < rows;
+                    const uint32_t *src = stage0 + (long long)i * stride4 + c * 32;
+                    uint32_t v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        v[e] = 0u;
+                        if (rok && s0 + e < p.S) v[e] = src[e];
+                    }
+                    pre[i] = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        };
+        auto store_chunk = [&](int c) {
+            uint32_t *dst = ring + srow * kPitch + (c & 1) * 32 + spiece * 4;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                dst[0] = pre[i].x;
+                dst[1] = pre[i].y;
+                dst[2] = pre[i].z;
+                dst[3] = pre[i].w;
+                dst += 4 * kPitch;
+            }
+        };
+
+        Acc<PREC> acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) acc[q].zero();
+
+        auto ckpt_for = [&](int s) {
+            const int c = min(max(s >> 5, 0), p.nchunks - 1);
+            return p.ckpt[(size_t)c * p.nchan + ch];
+        };
+
+        int staged_lo = (n_top >> 5) + 1;              // lowest chunk in the ring
+        __syncwarp();                                  // (the previous segment's reads are done)
+        load_chunk(staged_lo - 1);
+        store_chunk(staged_lo - 1);
+        staged_lo--;
+        load_chunk(staged_lo - 1);
+        double ck_next = ckpt_for(n_top);
+        __syncwarp();
+
+#pragma unroll 1
+        for (int tt = 0; tt < nper; tt++) {
+            const int s_hi = n_top - tt * DD;          // newest sample of the period (uniform)
+            const int s_lo = s_hi - DD + 1;
+            if ((s_lo >> 5) < staged_lo) {             // uniform: the period enters the next chunk down
+                __syncwarp();
+                store_chunk(staged_lo - 1);
+                staged_lo--;
+                load_chunk(staged_lo - 1);
+                __syncwarp();
+            }
+
+            // ---- table offsets of the period's samples
+            unsigned taddr[DD];
+            {
+                const double ck = ck_next;
+                ck_next = ckpt_for(s_lo - 1);
+                const int c = min(max(s_hi >> 5, 0), p.nchunks - 1);
+                unsigned long long x = phase_to_x56(ck) + (unsigned long long)((long long)(s_hi - (c << 5) + 1)) * dx;
+                bool near = exact_lane || !(ck >= 0.0);
+#pragma unroll
+                for (int j = 0; j < DD; j++) {
+                    const unsigned xh = (unsigned)(x >> 32);
+                    taddr[j] = lane_tab + ((xh >> 17) & 0x7f80u);   // entry (index) of this lane's copy
+                    near |= (xh * 256u + 256u) <= 256u;      // fraction within 2^-24 of an integer
+                    x -= dx;
+                }
+                if (__any_sync(0xffffffffu, near)) {
+                    if (near) {
+                        exact_period_indices(p.ckpt, p.tu_inc[ch], p.nchan, p.S, ch, s_hi, DD, scratch);
+#pragma unroll
+                        for (int j = 0; j < DD; j++) taddr[j] = lane_tab + ((unsigned)scratch[j] << 7);
+                    }
+                }
+            }
+
+            // ---- convert, mix, accumulate
+            if (s_lo >= 0 && (s_hi & (kRing - 1)) >= DD - 1 && !iqcorr) period_body<PREC, NTAPS, DD, true>(p, myrow, taddr, s_hi, ch, acc);
+            else period_body<PREC, NTAPS, DD, false>(p, myrow, taddr, s_hi, ch, acc);
+
+            // ---- the oldest role is complete: scale (:469,486), store, rotate
+            const int r_out = tt - (NQ - 1);
+            const int m = m_top - r_out;
+            if (r_out >= 0 && m < p.NO && lane_live) {
+                double2 o;
+                if constexpr (PREC == PREC_F64) {
+                    o = make_double2(__dmul_rn(acc[NQ - 1].i, 0.9 * 32768.0), __dmul_rn(acc[NQ - 1].q, 0.9 * 32768.0));
+                } else {
+                    o = make_double2((double)acc[NQ - 1].i * (0.9 * 32768.0), (double)acc[NQ - 1].q * (0.9 * 32768.0));
+                }
+                p.ds_out[(size_t)ch * p.max_ds + m] = o;
+            }
+#pragma unroll
+            for (int q = NQ - 1; q > 0; q--) acc[q] = acc[q - 1];
+            acc[0].zero();
+        }
+    }
+}
+
+}  // namespace stream
+}  // namespace bpsk
+}  // namespace jsdr

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/jsdrcuda.h"
 
@@ -39,6 +40,11 @@ void set_error(const char *fmt, ...);
 
 }  // namespace jsdr
 
+struct jsdr_prof_span {
+    int kind;
+    cudaEvent_t a, b;
+};
+
 struct jsdr_ctx {
     int device = 0;
     int sm_count = 0;
@@ -47,6 +53,10 @@ struct jsdr_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
+    // per-kernel timing: event pairs recorded around the launches while `profiling` is on
+    bool profiling = false;
+    std::vector<jsdr_prof_span> spans;       // recorded since the last read
+    std::vector<jsdr_prof_span> free_spans;  // event pairs ready for reuse
 
     int bind() const { return cudaSetDevice(device) == cudaSuccess ? JSDR_OK : JSDR_ECUDA; }
 };
@@ -64,6 +74,33 @@ static inline int launched(jsdr_ctx *ctx, const char *what)
     ctx->launches++;
     return JSDR_OK;
 }
+
+// Bracket one kernel launch with CUDA events on its stream when profiling is on.
+struct ProfScope {
+    jsdr_ctx *ctx;
+    cudaStream_t st;
+    jsdr_prof_span sp;
+    bool on;
+    ProfScope(jsdr_ctx *c, int kind, cudaStream_t s) : ctx(c), st(s), on(c->profiling)
+    {
+        if (!on) return;
+        if (!c->free_spans.empty()) {
+            sp = c->free_spans.back();
+            c->free_spans.pop_back();
+        } else {
+            cudaEventCreate(&sp.a);
+            cudaEventCreate(&sp.b);
+        }
+        sp.kind = kind;
+        cudaEventRecord(sp.a, st);
+    }
+    ~ProfScope()
+    {
+        if (!on) return;
+        cudaEventRecord(sp.b, st);
+        ctx->spans.push_back(sp);
+    }
+};
 
 // ---- device helpers -------------------------------------------------------
 #ifdef __CUDACC__

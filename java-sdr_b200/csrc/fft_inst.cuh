@@ -17,6 +17,7 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
     }
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
+    ProfScope prof(ctx, JSDR_K_FFT, st);
     kern<<<grid, P::T, P::SMEM, st>>>(a);
     return launched(ctx, "fft_kernel");
 }

@@ -52,6 +52,9 @@ struct jsdr_bpsk {
 
     double *d_tu_inc = nullptr;      // [nchan] tuPhaseInc
     unsigned long long *d_tu_dx = nullptr;   // [nchan] table-index step per sample, 8.48 fixed point
+    unsigned long long *d_tu_dx56 = nullptr; // [nchan] the same in 8.56 fixed point (streaming kernel)
+    int precision = 0;               // JSDR_PREC_F64 (exact) or JSDR_PREC_F32 (decimator in binary32)
+    int kernel_mode = 0;             // JSDR_KERNEL_AUTO / _TILE / _STREAM
     double *d_tu_phase0 = nullptr;   // [nchan] initial tuPhase (zeros)
     const double *d_tu_phase = nullptr;   // committed tuPhase: phase0 or the phase_end of the last plan used
     // Scout output ("plan") for one block.  Two of them: while the data kernels work

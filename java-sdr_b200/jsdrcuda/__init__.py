@@ -28,6 +28,8 @@ _SO = os.path.join(_ROOT, "libjsdrcuda.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "jsdrcuda.h")
 
 MEM_HOST, MEM_DEVICE = 0, 1
+PREC_F64, PREC_F32 = 0, 1
+KERNEL_AUTO, KERNEL_TILE, KERNEL_STREAM = 0, 1, 2
 INT_MIN = -2147483648
 
 
@@ -59,6 +61,8 @@ _SIGS = {
     "jsdr_ctx_destroy": [_vp],
     "jsdr_ctx_sync": [_vp],
     "jsdr_ctx_launch_count": [_vp, C.POINTER(_i64)],
+    "jsdr_ctx_profile": [_vp, _i],
+    "jsdr_ctx_profile_read": [_vp, _vp, _vp, _i],
     "jsdr_host_alloc": [_vp, C.c_size_t, _pp],
     "jsdr_host_free": [_vp, _vp],
     "jsdr_dev_alloc": [_vp, C.c_size_t, _pp],
@@ -78,6 +82,8 @@ _SIGS = {
     "jsdr_bpsk_destroy": [_vp],
     "jsdr_bpsk_set_stages": [_vp, _i],
     "jsdr_bpsk_set_tuning": [_vp, _i, _d],
+    "jsdr_bpsk_set_precision": [_vp, _i],
+    "jsdr_bpsk_set_kernel": [_vp, _i],
     "jsdr_bpsk_set_ds_filter": [_vp, _vp, _i],
     "jsdr_bpsk_receive_f32": [_vp, _vp, _i, _i64, _i],
     "jsdr_bpsk_receive_s16": [_vp, _vp, _i, _i64, _i, _i, _i],
@@ -217,6 +223,19 @@ class Context:
         n = C.c_int64()
         _ck(lib().jsdr_ctx_launch_count(self.h, C.byref(n)))
         return n.value
+
+    KINDS = ("fft", "mixdecim", "matched", "timing", "scout", "other")
+
+    def profile(self, enable: bool = True):
+        """Bracket every kernel launch with CUDA events on its own stream (bench.py)."""
+        _ck(lib().jsdr_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kind: (total ms, launches)} since the last read; waits for the device."""
+        ms = np.zeros(len(self.KINDS), dtype=np.float64)
+        cnt = np.zeros(len(self.KINDS), dtype=np.int64)
+        _ck(lib().jsdr_ctx_profile_read(self.h, _ptr(ms), _ptr(cnt), len(self.KINDS)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KINDS)}
 
     def dev_alloc(self, nbytes: int) -> DevBuf:
         return DevBuf(self, nbytes)
@@ -369,6 +388,12 @@ class FUNcubeBPSKDemod:
     def set_tuning(self, chan: int, hz: float):
         _ck(lib().jsdr_bpsk_set_tuning(self.h, chan, hz))
         self.tuning[chan] = hz
+
+    def set_precision(self, precision: int):
+        _ck(lib().jsdr_bpsk_set_precision(self.h, precision))
+
+    def set_kernel(self, mode: int):
+        _ck(lib().jsdr_bpsk_set_kernel(self.h, mode))
 
     def set_ds_filter(self, taps: np.ndarray):
         t = np.ascontiguousarray(taps, dtype=np.float64)

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Kernel-level timings on one GPU (CUDA events on the library's stream).
+  python tools/kbench.py mix   [nchan] [S]      tuner+decimator: tile / stream f64 / stream f32
+  python tools/kbench.py fft   [n ...]          FFT+PSD per length (s16 and f32 input)
+Prints achieved GB/s of algorithmic bytes and the fraction of MEASURED_PEAKS.json."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "java-sdr_b200")):
+    sys.path.insert(0, p)
+import jsdrcuda as J
+
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+
+
+def time_ms(ctx, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(reps):
+        fn()
+    return ctx.timer_stop_ms() / reps
+
+
+def mix(nchan=4096, S=131072, rate=192000, ntaps=64):
+    ctx = J.Context(0)
+    D = rate // 9600
+    rng = np.random.default_rng(1)
+    tun = rng.uniform(2000, 90000, nchan)
+    taps = J.design_lowpass(ntaps, 4800.0, rate) if ntaps != 27 else None
+    d_raw = ctx.dev_alloc(nchan * S * 4)
+    tile = rng.integers(-20000, 20000, (64, 2 * S)).astype(np.int16)
+    for c0 in range(0, nchan, 64):
+        d_raw.upload(tile[: min(64, nchan - c0)], offset=c0 * S * 4)
+    bytes_ = nchan * S * 4 + nchan * (S // D) * 16
+    for name, kern, prec in (("tile f64", J.KERNEL_TILE, J.PREC_F64), ("stream f64", J.KERNEL_STREAM, J.PREC_F64),
+                             ("stream f32", J.KERNEL_STREAM, J.PREC_F32)):
+        bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate), tuning=tun, max_block=S, stages=1)
+        if taps is not None:
+            bank.set_ds_filter(taps)
+        bank.set_kernel(kern)
+        bank.set_precision(prec)
+        ms = time_ms(ctx, lambda: bank.receive_dev(d_raw, S, S, s16=True))
+        gbs = bytes_ / ms / 1e6
+        print(f"mix {name:10s} nchan={nchan} S={S} taps={ntaps} D={D}: {ms:8.3f} ms  {nchan * S / ms / 1e3:9.1f} Msamples/s  "
+              f"{gbs:7.1f} GB/s  frac {gbs / PEAK:.3f}", flush=True)
+        bank.close()
+    ctx.close()
+
+
+def fft(ns, total=1 << 28):
+    ctx = J.Context(0)
+    rng = np.random.default_rng(2)
+    for n in ns:
+        batch = max(1, total // n)
+        f = J.fft(ctx, None, J.AudioDescriptor(192000), max_batch=batch, n=n)
+        d_in = ctx.dev_alloc(batch * n * 8)
+        d_in.upload(rng.integers(-20000, 20000, 1 << 22).astype(np.int16))
+        d_psd = ctx.dev_alloc(batch * (n + 2) * 4)
+        d_pk = ctx.dev_alloc(batch * 4)
+        for s16 in (True, False):
+            ms = time_ms(ctx, lambda: f.receive_dev(d_in, batch, d_psd, d_pk, s16=s16))
+            b = batch * n * ((4 if s16 else 8) + 4)
+            print(f"fft n={n:6d} batch={batch:7d} {'s16' if s16 else 'f32'}: {ms:8.3f} ms  {batch * n / ms / 1e3:9.1f} Msamples/s  "
+                  f"{b / ms / 1e6:7.1f} GB/s  frac {b / ms / 1e6 / PEAK:.3f}", flush=True)
+        for d in (d_in, d_psd, d_pk):
+            d.free()
+        f.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "mix"
+    if what == "mix":
+        a = [int(x) for x in sys.argv[2:]]
+        mix(*a)
+    else:
+        fft([int(x) for x in sys.argv[2:]] or [256, 1024, 4096, 9600, 16384, 19200])
