@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--fft-n", type=int, default=4096, help="block length (complex samples)")
     ap.add_argument("--blocks", type=int, default=128, help="blocks per channel per step")
     ap.add_argument("--taps", type=int, default=64, help="decimator taps (config 4: 64)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="tuner+decimator arithmetic of the headline run: f64 = the reference's binary64, bit-exact")
     ap.add_argument("--e2e-channels", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -60,6 +62,16 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def measured_traffic():
+    """DRAM bytes per input sample of the two data kernels, from the committed ncu --set full
+    captures (profiles/traffic.json; written by tools/ncu_summary.py runs)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def workload_name(a):
@@ -207,6 +219,7 @@ def main():
     f = J.fft(ctx, None, adsc, max_batch=batch, n=n)
     bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S, stages=1)
     bank.set_ds_filter(taps)
+    bank.set_precision(J.PREC_F32 if a.precision == "f32" else J.PREC_F64)
 
     d_raw = ctx.dev_alloc(samples * 4)
     d_psd = ctx.dev_alloc(batch * (n + 2) * 4)
@@ -233,30 +246,32 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
+    ctx.profile(True)            # CUDA events around every kernel launch, on the stream it is launched on
+    ctx.profile_read()
     ctx.timer_start()
     for _ in range(a.steps):
         step()
     ms = ctx.timer_stop_ms()
     launches = ctx.launch_count() - l0
+    kern = ctx.profile_read()    # {kind: (total ms, launches)} inside the timed region
+    ctx.profile(False)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    fft_ms = kern["fft"][0] / max(kern["fft"][1], 1)
+    mix_ms = kern["mixdecim"][0] / max(kern["mixdecim"][1], 1)
+    scout_ms = kern["scout"][0] / max(kern["scout"][1], 1)
 
-    # ---- dominant kernel alone (FFT+PSD), CUDA events on the launching stream
+    # ---- the other decimator arithmetic, same pipeline, for the record (rank-local, few steps)
+    other = "f32" if a.precision == "f64" else "f64"
+    bank.set_precision(J.PREC_F32 if other == "f32" else J.PREC_F64)
     for _ in range(2):
-        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
+        step()
     ctx.sync()
     ctx.timer_start()
-    for _ in range(a.steps):
-        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
-    fft_ms = ctx.timer_stop_ms() / a.steps
-    # ---- second kernel alone (tuner + decimator incl. its phase scout)
-    for _ in range(2):
-        bank.receive_dev(d_raw, S, S, s16=True)
-    ctx.sync()
-    ctx.timer_start()
-    for _ in range(a.steps):
-        bank.receive_dev(d_raw, S, S, s16=True)
-    mix_ms = ctx.timer_stop_ms() / a.steps
+    for _ in range(max(2, a.steps // 2)):
+        step()
+    other_ms = ctx.timer_stop_ms() / max(2, a.steps // 2)
+    bank.set_precision(J.PREC_F32 if a.precision == "f32" else J.PREC_F64)
 
     # ---- end to end through the C ABI with host (pinned) buffers
     e_ch = min(a.e2e_channels, nchan)
@@ -288,9 +303,9 @@ def main():
     t_step = ms / a.steps
     if dist is not None:
         import torch
-        t = torch.tensor([t_step, fft_ms, mix_ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step, fft_ms, mix_ms, e2e_s = [float(x) for x in t.tolist()]
+        t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms = [float(x) for x in t.tolist()]
         cnt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches = int(cnt.item())
@@ -298,32 +313,49 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         value = world * samples / (t_step * 1e-3) / 1e6
+        nout = nchan * (S // D)
         fft_bytes = samples * 8 + batch * 8            # s16 in (4 B) + float PSD out (4 B) per sample, + 2 floats per block
-        mix_bytes = samples * 4 + samples // D * 16 + samples // 32 * 16   # s16 in + complex double out (+ phase checkpoints r/w)
-        fft_gbs = fft_bytes / (fft_ms * 1e-3) / 1e9
-        mix_gbs = (samples * 4 + samples // D * 16) / (mix_ms * 1e-3) / 1e9
-        step_bytes = samples * 4 + samples * 4 + samples // D * 16
+        mix_bytes = samples * 4 + nout * 16            # s16 in + complex double out
+        step_bytes = samples * 4 + samples * 4 + nout * 16
+        traffic = measured_traffic()
+        kernels = [
+            {"kernel": "k_mixdecim_stream (NCO mix + %d-tap FIR decimate x%d, %s)" % (a.taps, D, a.precision),
+             "ms_per_launch": round(mix_ms, 4), "algorithmic_bytes_per_launch": mix_bytes,
+             "traffic": traffic.get("mixdecim_bytes_per_sample") and int(traffic["mixdecim_bytes_per_sample"] * samples)},
+            {"kernel": "fft_kernel (FFT N=%d + PSD, s16 in)" % n,
+             "ms_per_launch": round(fft_ms, 4), "algorithmic_bytes_per_launch": fft_bytes,
+             "traffic": traffic.get("fft_bytes_per_sample") and int(traffic["fft_bytes_per_sample"] * samples)},
+        ]
+        for k in kernels:
+            k["achieved"] = round(k["algorithmic_bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9, 1)
+            k["frac"] = round(k["achieved"] / peak, 4)
+        kernels.sort(key=lambda k: -k["ms_per_launch"])
+        dom = kernels[0]
         line = {
             "metric": "Msamples/s (complex IQ) through mix+FIR+FFT",
             "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(t_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (FFT/PSD) + f64 (tuner/decimator, reference order)", "data": "synthetic",
+            "dtype": "f32 (FFT/PSD) + %s (tuner/decimator%s)" % (a.precision, ", reference order, bit-exact" if a.precision == "f64" else ""),
+            "data": "synthetic",
             "config": {"workload": workload_name(a), "channels_per_gpu": nchan, "blocks_per_channel": nblk,
                        "fft_n": n, "rate": RATE, "decimation": D, "taps": a.taps,
                        "l2": "inputs larger than L2 (%.1f GiB resident per GPU)" % (samples * 4 / 2 ** 30),
                        "sharding": "channels split across ranks, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "fft_kernel (FFT+PSD, s16 in)", "achieved": round(fft_gbs, 1),
-                         "peak": peak, "unit": "GB/s", "frac": round(fft_gbs / peak, 4), "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
+                         "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
                          "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json)",
-                         "algorithmic_bytes_per_launch": fft_bytes, "ms_per_launch": round(fft_ms, 4),
-                         "other_kernels": [{"kernel": "k_tuner_scout + k_mixdecim + k_tuner_tail (tuner + decimator)",
-                                            "achieved": round(mix_gbs, 1), "frac": round(mix_gbs / peak, 4),
-                                            "ms_per_launch": round(mix_ms, 4),
-                                            "algorithmic_bytes_per_launch": samples * 4 + samples // D * 16}],
+                         "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                         "ms_per_launch": dom["ms_per_launch"],
+                         "timing": "CUDA events around each launch on its own stream, averaged over the timed region",
+                         "other_kernels": kernels[1:] + [{"kernel": "k_tuner_scout (exact tuner phase replay, side stream, overlapped)",
+                                                          "ms_per_launch": round(scout_ms, 4)}],
                          "pipeline": {"algorithmic_bytes_per_step_fused": step_bytes,
                                       "achieved": round(step_bytes / (t_step * 1e-3) / 1e9, 1),
                                       "frac": round(step_bytes / (t_step * 1e-3) / 1e9 / peak, 4),
                                       "note": "4 B in (read once) + 4 B PSD + 16/D B decimated out per sample"}},
+            "variants": {"decimator_" + other: {"value": round(world * samples / (other_ms * 1e-3) / 1e6, 1),
+                                                "unit": "Msamples/s", "ms_per_step": round(other_ms, 4),
+                                                "note": "same pipeline with the tuner+decimator in %s" % other}},
             "e2e": {"value": round(world * e2e_samples / e2e_s / 1e6, 1), "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "sample": f"{e_ch} channels x {nblk} blocks per rank through jsdr_pump_receive_s16 + jsdr_bpsk_read_ds with pinned host buffers"},

@@ -1,5 +1,6 @@
 // api.cu — context, memory and timing entry points of libjsdrcuda.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -61,6 +62,7 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
         // the whole grid of the data kernel that runs beside it
         int lo = 0, hi = 0;
         JSDR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        if (getenv("JSDR_SIDE_PRIORITY") && atoi(getenv("JSDR_SIDE_PRIORITY")) == 0) hi = lo;   // (tuning aid)
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi));
     }
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t0));

@@ -130,27 +130,36 @@ __device__ __forceinline__ void raw_to_iq(typename RawT<FMT>::type w, int ic, in
 // side stream, one block ahead of the data (see bpsk_receive), and costs almost no
 // issue slots, so it hides behind the data kernels.
 // Two reference steps in three dependent additions.  With 0 < inc < pi a wrap cannot follow a
-// wrap, so the pair is one of (no wrap, no wrap), (wrap, none), (none, wrap); which one is read
-// off the phase BEFORE the pair (p > 2pi-inc, p > 2pi-2inc), off the critical path, and the
-// additions are the reference's own: t1 = p+inc; t2 = t1 + (-2pi | inc); t3 = t2 + (inc | -2pi | 0).
-// The prediction compares against rounded thresholds; when p is within 2^-40 of one of them the
-// 32-sample chunk is replayed step by step instead (checked once per chunk, off the chain).
-__device__ __forceinline__ double phase_step2(double p, double inc, double th1, double th2, bool &risky)
+// wrap, so the pair is one of (no wrap, no wrap), (wrap, none), (none, wrap); which one is
+// PREDICTED from the phase before the pair (p > 2pi-inc, p > 2pi-2inc), off the critical path, and
+// the additions are the reference's own: t1 = p+inc; t2 = t1 + (-2pi | inc); t3 = t2 + (inc | -2pi | 0).
+// The reference's own comparisons (t1 > 2pi, t2 > 2pi) are then evaluated behind the chain and
+// compared with the prediction; a mismatch (p within an ulp or two of a threshold) marks the
+// 32-sample chunk, which is then replayed step by step.  So the result is the reference's sequence
+// by construction, not by an error bound.
+__device__ __forceinline__ double phase_step2(double p, double inc, double th1, double th2, bool &bad)
 {
     const bool m1 = p > th1, m2 = p > th2;
-    risky |= (fabs(__dadd_rn(p, -th1)) < 9.094947017729282e-13) | (fabs(__dadd_rn(p, -th2)) < 9.094947017729282e-13);
     const double s2 = m1 ? -kTwoPi : inc;
     const double s3 = m1 ? inc : (m2 ? -kTwoPi : 0.0);
     const double t1 = __dadd_rn(p, inc);
     const double t2 = __dadd_rn(t1, s2);
-    return __dadd_rn(t2, s3);
+    const double t3 = __dadd_rn(t2, s3);
+    const bool w1 = t1 > kTwoPi;                 // :385 as the reference evaluates it
+    const bool w2 = !w1 && (t2 > kTwoPi);        // second step's test (after a wrap t2 <= inc < 2pi: never)
+    bad |= (w1 != m1) | (w2 != (m2 && !m1));
+    return t3;
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int kScoutThreads = 512;
+
+// One thread per channel; 512 channels per CTA, so that a bank's replay occupies a handful of
+// SMs (which the streaming data kernel leaves free) instead of one warp on every SM.
+__global__ void __launch_bounds__(kScoutThreads)
 k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_in,
               double *__restrict__ phase_out, double *__restrict__ ckpt, int nchan, int S)
 {
-    const int ch = blockIdx.x * 32 + threadIdx.x;
+    const int ch = blockIdx.x * kScoutThreads + threadIdx.x;
     if (ch >= nchan) return;
     double p = phase_in[ch];
     const double inc = inc_[ch];
@@ -160,10 +169,10 @@ k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_
         for (int w = 0; w < nfull; w++) {
             ckpt[(size_t)w * nchan + ch] = p;
             const double p0 = p;
-            bool risky = false;
+            bool bad = false;
 #pragma unroll
-            for (int j = 0; j < 16; j++) p = phase_step2(p, inc, th1, th2, risky);
-            if (risky) {
+            for (int j = 0; j < 16; j++) p = phase_step2(p, inc, th1, th2, bad);
+            if (bad) {
                 p = p0;
                 for (int j = 0; j < 32; j++) p = phase_step(p, inc);
             }
@@ -604,7 +613,7 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
 {
     jsdr_ctx *ctx = b->ctx;
     ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
-    k_tuner_scout<<<(b->nchan + 31) / 32, 32, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+    k_tuner_scout<<<(b->nchan + kScoutThreads - 1) / kScoutThreads, kScoutThreads, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
                                                              b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
@@ -665,7 +674,10 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
         attr_done = true;
     }
     const int warps = sp.ncw * sp.nseg;
-    const int grid = std::min((warps + W - 1) / W, ctx->sm_count);   // one CTA per SM, warps loop over segments
+    // one CTA per SM, warps loop over segments; the SMs the phase scout needs (512 channels per
+    // CTA, on the high-priority side stream) are left free so that the two never share an SM
+    const int scout_ctas = (sp.nchan + kScoutThreads - 1) / kScoutThreads;
+    const int grid = std::min((warps + W - 1) / W, std::max(ctx->sm_count - scout_ctas, ctx->sm_count / 2));
     ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
     kern<<<grid, W * 32, smem, ctx->stream>>>(sp);
     return launched(ctx, "k_mixdecim_stream");
