@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -146,20 +147,31 @@ __device__ __forceinline__ double phase_step2(double p, double inc, double th1, 
     const double t2 = __dadd_rn(t1, s2);
     const double t3 = __dadd_rn(t2, s3);
     const bool w1 = t1 > kTwoPi;                 // :385 as the reference evaluates it
-    const bool w2 = !w1 && (t2 > kTwoPi);        // second step's test (after a wrap t2 <= inc < 2pi: never)
-    bad |= (w1 != m1) | (w2 != (m2 && !m1));
+    const bool w2 = t2 > kTwoPi;                 // the second step's test when the first did not wrap
+    bad |= (w1 != m1) | (!m1 & (w2 != m2));
     return t3;
 }
 
-constexpr int kScoutThreads = 512;
+constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
 
-// One thread per channel; 512 channels per CTA, so that a bank's replay occupies a handful of
+static int scout_threads()
+{
+    static int t = 0;
+    if (!t) {
+        const char *e = getenv("JSDR_SCOUT_THREADS");          // (tuning aid)
+        t = e ? atoi(e) : 384;
+        if (t < 32 || t > kScoutThreads || (t & 31)) t = 384;
+    }
+    return t;
+}
+
+// One thread per channel; a few hundred channels per CTA, so that a bank's replay occupies a handful of
 // SMs (which the streaming data kernel leaves free) instead of one warp on every SM.
 __global__ void __launch_bounds__(kScoutThreads)
 k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_in,
               double *__restrict__ phase_out, double *__restrict__ ckpt, int nchan, int S)
 {
-    const int ch = blockIdx.x * kScoutThreads + threadIdx.x;
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchan) return;
     double p = phase_in[ch];
     const double inc = inc_[ch];
@@ -613,7 +625,7 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
 {
     jsdr_ctx *ctx = b->ctx;
     ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
-    k_tuner_scout<<<(b->nchan + kScoutThreads - 1) / kScoutThreads, kScoutThreads, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+    k_tuner_scout<<<(b->nchan + scout_threads() - 1) / scout_threads(), scout_threads(), 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
                                                              b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
@@ -674,10 +686,7 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
         attr_done = true;
     }
     const int warps = sp.ncw * sp.nseg;
-    // one CTA per SM, warps loop over segments; the SMs the phase scout needs (512 channels per
-    // CTA, on the high-priority side stream) are left free so that the two never share an SM
-    const int scout_ctas = (sp.nchan + kScoutThreads - 1) / kScoutThreads;
-    const int grid = std::min((warps + W - 1) / W, std::max(ctx->sm_count - scout_ctas, ctx->sm_count / 2));
+    const int grid = std::min((warps + W - 1) / W, sp.grid);
     ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
     kern<<<grid, W * 32, smem, ctx->stream>>>(sp);
     return launched(ctx, "k_mixdecim_stream");
@@ -701,10 +710,13 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     sp.n0 = mp.n0;
     sp.NO = mp.NO;
     sp.ncw = (mp.nchan + 31) / 32;
-    // segments: a few per resident warp so that the SMs stay evenly loaded, but long enough
-    // that the NQ-1 warm-up periods of a segment do not matter
-    const int want_warps = b->ctx->sm_count * stream::kWarps * 3;
-    int nseg = (want_warps + sp.ncw - 1) / sp.ncw;
+    // one CTA per SM, warps loop over segments; the SMs the phase scout needs (on the
+    // high-priority side stream) are left free so that the two never share an SM.  Segments:
+    // about three per resident warp, their count chosen so that the last wave is full.
+    const int scout_ctas = (mp.nchan + scout_threads() - 1) / scout_threads();
+    sp.grid = std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
+    const int resident = sp.grid * stream::kWarps;
+    int nseg = std::max(1, 3 * resident / sp.ncw);
     int R = (mp.NO + nseg - 1) / nseg;
     if (R < 64) R = 64;
     sp.R = R;

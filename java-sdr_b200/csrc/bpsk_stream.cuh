@@ -47,6 +47,7 @@ struct Params {
     const double2 *hist_in;             // [nchan][kMaxDsTaps], entry k is local sample k-H
     const double2 *cossin;              // [257] (cos, sin); entry 256 = (1, 1), the mixer bypass
     int n0, NO, R, nseg, ncw;           // first output's sample, outputs, outputs per segment, segments, channel groups
+    int grid;                           // CTAs to launch (host side only)
     double2 *ds_out;
     int max_ds;
     double taps[kMaxTaps];
