@@ -212,8 +212,11 @@ def main():
     batch = nchan * nblk
     samples = nchan * S
 
-    rng = np.random.Generator(np.random.PCG64(7 + rank))
-    tuning = rng.uniform(2000, 90000, nchan)
+    # weak scaling: every rank owns a.channels channels of a (world * a.channels)-channel bank;
+    # a channel's tuning depends on its global index only (jsdrcuda/sharding.py)
+    from jsdrcuda import sharding
+    first, _ = sharding.partition(world * nchan, world, rank)
+    tuning = sharding.channel_tuning(first, nchan)
     taps = J.design_lowpass(a.taps, 4800.0, RATE)
 
     f = J.fft(ctx, None, adsc, max_batch=batch, n=n)
@@ -301,14 +304,13 @@ def main():
 
     # ---- reduce over ranks: max time, summed work
     t_step = ms / a.steps
+    dev = None
     if dist is not None:
         import torch
-        t = torch.tensor([t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms = [float(x) for x in t.tolist()]
-        cnt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        launches = int(cnt.item())
+        dev = torch.device("cuda", local)
+    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms), launches = sharding.reduce_timing(
+        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms], launches)
+    launches = int(launches)
 
     if rank == 0:
         peak, peak_src = peaks()
