@@ -65,6 +65,12 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
         if (getenv("JSDR_SIDE_PRIORITY") && atoi(getenv("JSDR_SIDE_PRIORITY")) == 0) hi = lo;   // (tuning aid)
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi));
     }
+    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+        JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk_in[i], cudaEventDisableTiming));
+        JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk_done[i], cudaEventDisableTiming));
+    }
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t0));
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t1));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -88,6 +94,12 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
             cudaEventDestroy(sp.a);
             cudaEventDestroy(sp.b);
         }
+    for (int i = 0; i < 16; i++) {
+        cudaEventDestroy(ctx->ev_chunk_in[i]);
+        cudaEventDestroy(ctx->ev_chunk_done[i]);
+    }
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->side);
     delete ctx;
@@ -100,6 +112,7 @@ extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaStreamSynchronize(ctx->side));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     return JSDR_OK;
 }
 

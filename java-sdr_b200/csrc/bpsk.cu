@@ -1221,13 +1221,41 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
         f->out_cap = psd_elems * sizeof(float);
     }
     if (!f->d_peak) JSDR_CUDA(cudaMalloc(&f->d_peak, sizeof(int32_t) * (size_t)f->max_batch));
-    job.d_psd = f->d_out;
-    job.d_peak = f->d_peak;
-    JSDR_TRY(bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job));
-    JSDR_CUDA(cudaMemcpyAsync(psd, f->d_out, psd_elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (peak_bin)
-        JSDR_CUDA(cudaMemcpyAsync(peak_bin, f->d_peak, sizeof(int32_t) * (size_t)batch,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t in_bytes = (size_t)b->nchan * (size_t)S * 4;
+    if (b->in_cap < in_bytes) {
+        cudaFree(b->d_in);
+        b->d_in = nullptr;
+        b->in_cap = 0;
+        JSDR_CUDA(cudaMalloc(&b->d_in, in_bytes));
+        b->in_cap = in_bytes;
+    }
+    // Host path, pipelined over channel chunks: PCIe is full duplex, so the upload of chunk
+    // c+1 (copy_in stream) runs beside the FFT of chunk c (main stream) and the download of
+    // the PSD of chunk c-1 (copy_out stream).  The tuner bank runs once the whole batch is in.
+    const int nchunk = std::min(16, std::max(1, b->nchan / 8));
+    JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));            // staging buffers are free again
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
+    for (int c = 0; c < nchunk; c++) {
+        const int c0 = (int)((long long)b->nchan * c / nchunk), c1 = (int)((long long)b->nchan * (c + 1) / nchunk);
+        if (c1 == c0) continue;
+        const size_t in_off = (size_t)c0 * (size_t)S * 4, in_len = (size_t)(c1 - c0) * (size_t)S * 4;
+        const size_t blk0 = (size_t)c0 * nblocks, nblk = (size_t)(c1 - c0) * nblocks;
+        JSDR_CUDA(cudaMemcpyAsync((char *)b->d_in + in_off, (const char *)raw + in_off, in_len,
+                                  cudaMemcpyHostToDevice, ctx->copy_in));
+        JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_in[c], ctx->copy_in));
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk_in[c], 0));
+        JSDR_TRY(fft::launch(f, (const char *)b->d_in + in_off, fft::IN_S16, (int)nblk, f->d_out + blk0 * (f->n + 2),
+                             f->d_peak + blk0, fft::OUT_PSD, 0, 0, ctx->stream));
+        JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_done[c], ctx->stream));
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_chunk_done[c], 0));
+        JSDR_CUDA(cudaMemcpyAsync(psd + blk0 * (f->n + 2), f->d_out + blk0 * (f->n + 2), nblk * (f->n + 2) * sizeof(float),
+                                  cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (peak_bin)
+            JSDR_CUDA(cudaMemcpyAsync(peak_bin + blk0, f->d_peak + blk0, sizeof(int32_t) * nblk,
+                                      cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    JSDR_TRY(bpsk_receive<FMT_S16>(b, b->d_in, (int)S, S, 0, 0, JSDR_MEM_DEVICE));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
 }

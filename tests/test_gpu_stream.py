@@ -106,3 +106,26 @@ def test_stream_f32_within_tolerance(ctx, rate, ntaps):
     assert worst <= 1e-4, worst
     assert worst <= 2e-6, worst       # what binary32 actually achieves here
     a.close()
+
+
+def test_pump_host_path_chunked_equals_separate_handlers(ctx):
+    """jsdr_pump_receive_s16 with host buffers pipelines the batch over channel chunks
+    (upload / FFT / download overlapped); results must equal the two handlers run apart."""
+    rate, nchan, n, nblk = 192000, 44, 4096, 2
+    rng = np.random.default_rng(21)
+    tun = rng.uniform(2000, 90000, nchan)
+    raw = rng.integers(-30000, 30000, (nchan, nblk * n * 2)).astype(np.int16)
+    adsc = J.AudioDescriptor(rate)
+    f = J.fft(ctx, None, adsc, max_batch=nchan * nblk, n=n)
+    b1 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=nblk * n, stages=1)
+    b2 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=nblk * n, stages=1)
+    psd = np.empty((nchan * nblk, n + 2), np.float32)
+    pk = np.empty(nchan * nblk, np.int32)
+    for k in range(2):
+        J.pump_receive_s16(f, b1, raw, nblk, psd, pk)
+        psd2, pk2 = f.receive_batch(raw.reshape(nchan * nblk, 2 * n), s16=True)
+        assert np.array_equal(psd, psd2) and np.array_equal(pk, pk2)
+        b2.receive_raw(raw)
+        assert np.array_equal(b1.read_ds(), b2.read_ds())
+    for h in (f, b1, b2):
+        h.close()
