@@ -298,10 +298,13 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
 #pragma unroll
         for (int q = 0; q < NQ; q++) acc[q].zero();
 
-        auto ckpt_for = [&](int s) {
-            const int c = min(max(s >> 5, 0), p.nchunks - 1);
-            return p.ckpt[(size_t)c * p.nchan + ch];
-        };
+        // x = tuPhase*256/2pi (8.56 fixed point) of the newest sample of the current period.  It is
+        // re-anchored at an exact checkpoint every kReanchor periods and stepped by integer adds
+        // in between (at most kReanchor*D + 32 steps from an anchor: drift < 2^-36, guard 2^-24).
+        constexpr int kReanchor = 12;
+        const unsigned long long dxD = dx * (unsigned long long)DD;
+        unsigned long long x_top = 0;
+        bool bad_anchor = false;
 
         int staged_lo = (n_top >> 5) + 1;              // lowest chunk in the ring
         __syncwarp();                                  // (the previous segment's reads are done)
@@ -309,7 +312,6 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
         store_chunk(staged_lo - 1);
         staged_lo--;
         load_chunk(staged_lo - 1);
-        double ck_next = ckpt_for(n_top);
         __syncwarp();
 
 #pragma unroll 1
@@ -324,14 +326,18 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
                 __syncwarp();
             }
 
-            // ---- table offsets of the period's samples
+            // ---- table addresses of the period's samples
             unsigned taddr[DD];
             {
-                const double ck = ck_next;
-                ck_next = ckpt_for(s_lo - 1);
-                const int c = min(max(s_hi >> 5, 0), p.nchunks - 1);
-                unsigned long long x = phase_to_x56(ck) + (unsigned long long)((long long)(s_hi - (c << 5) + 1)) * dx;
-                bool near = exact_lane || !(ck >= 0.0);
+                if (tt % kReanchor == 0) {             // uniform
+                    const int c = min(max(s_hi >> 5, 0), p.nchunks - 1);
+                    const double ck = p.ckpt[(size_t)c * p.nchan + ch];
+                    x_top = phase_to_x56(ck) + (unsigned long long)((long long)(s_hi - (c << 5) + 1)) * dx;
+                    bad_anchor = !(ck >= 0.0);
+                }
+                unsigned long long x = x_top;
+                x_top -= dxD;
+                bool near = exact_lane || bad_anchor;
 #pragma unroll
                 for (int j = 0; j < DD; j++) {
                     const unsigned xh = (unsigned)(x >> 32);
