@@ -129,6 +129,15 @@ int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double *tuning_hz
 int jsdr_bpsk_destroy(jsdr_bpsk *b);
 int jsdr_bpsk_set_stages(jsdr_bpsk *b, int stages);
 int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz);       /* :174-189 */
+/* The FFT auto-tune variant, doBufferFFT (FUNcubeBPSKDemod.java:406-464; config keys
+ * "FUNcube<i>-bpsk-dofft" / "-upper", :198-200): when dofft is set every receive call
+ * must carry exactly max_block_samples samples (the transform length is the block
+ * length, :421).  Forward transform in binary64, 100-bin boxcar arg-max over the lower
+ * (or, do_upper, upper) quarter band, smoothed / gated / clamped centre bin, 204 bins
+ * moved to DC, inverse transform scaled by 1/n, decimator fed (re, re) (:461-463).
+ * read_centre returns what the reference publishes as "<name>-bpsk-centre" (:456). */
+int jsdr_bpsk_set_autotune(jsdr_bpsk *b, int dofft, int do_upper);
+int jsdr_bpsk_read_centre(jsdr_bpsk *b, int32_t *centre_bin /* nchan */);
 /* Arithmetic of the tuner + decimator stage.  JSDR_PREC_F64 (default) is the
  * reference's binary64 in the reference's operation order: every output is
  * bit-identical to the Java arithmetic, and the bits that follow are exact.

@@ -24,6 +24,7 @@
 
 #include <vector>
 
+#include "fft_generic.cuh"
 #include "handles.h"
 
 namespace jsdr {
@@ -437,6 +438,124 @@ __global__ void k_tuner_tail(const MixParams p)
 namespace jsdr {
 namespace bpsk {
 
+
+// ------------------------------------------------------------------ auto-tune (doBufferFFT, :406-464)
+// :417-420 (double)buf[..] into the forward transform's input
+template <int FMT>
+__global__ void __launch_bounds__(256) k_at_load(const void *__restrict__ in, long long chan_stride, int S, int nchan,
+                                                 int ic, int qc, double2 *__restrict__ out)
+{
+    typedef typename RawT<FMT>::type raw_t;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nchan * S) return;
+    const int ch = (int)(i / S), n = (int)(i - (long long)ch * S);
+    double xi, xq;
+    raw_to_iq<FMT>(reinterpret_cast<const raw_t *>(in)[(long long)ch * chan_stride + n], ic, qc, xi, xq);
+    out[i] = make_double2(xi, xq);
+}
+
+// :425-458 for one channel per CTA: magnitude, 100-bin boxcar sums in the reference's summation
+// order, first strict maximum, the smoothing / gate / clamp of the centre bin, and the copy of
+// 204 bins to DC of the (pre-zeroed) inverse transform's input.
+__global__ void __launch_bounds__(256) k_at_search(const double2 *__restrict__ fwd, double2 *__restrict__ rev, int N,
+                                                   int doUp, AutoTuneState *__restrict__ state)
+{
+    extern __shared__ double s_psd[];                  // psd[lo .. hi)
+    __shared__ unsigned long long s_max;
+    __shared__ int s_idx;
+    __shared__ int s_centre;
+    const int ch = blockIdx.x, tid = threadIdx.x;
+    const double2 *x = fwd + (size_t)ch * N;
+    const int beg = doUp ? N / 4 : 0, end = doUp ? N / 2 : N / 4;
+    const int lo = max(beg + 75 - 50, 0), hi = max(min(end - 75 + 50, N / 2), lo);   // psd[] range the sums touch
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+        const double2 v = x[i];
+        s_psd[i - lo] = __dsqrt_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)));   // :426
+    }
+    if (tid == 0) {
+        s_max = 0ull;
+        s_idx = 0x7fffffff;
+    }
+    __syncthreads();
+    auto boxcar = [&](int i) {                         // :436-439, j ascending from a zero start
+        double a = 0.0;
+        for (int j = i - 50; j < i + 50; j++) a = __dadd_rn(a, s_psd[j - lo]);
+        return a;
+    };
+    double best = 0.0;                                 // :429 maxBin starts at 0.0; strict '<' (:440)
+    int best_i = 0x7fffffff;
+    for (int i = beg + 75 + tid; i < end - 75; i += blockDim.x) {
+        const double a = boxcar(i);
+        if (best < a) {
+            best = a;
+            best_i = i;
+        }
+    }
+    // sums are non-negative: their bit patterns order like the values
+    if (best_i != 0x7fffffff) atomicMax(&s_max, (unsigned long long)__double_as_longlong(best));
+    __syncthreads();
+    if (best_i != 0x7fffffff && (unsigned long long)__double_as_longlong(best) == s_max) atomicMin(&s_idx, best_i);
+    __syncthreads();
+    if (tid == 0) {
+        AutoTuneState st = state[ch];
+        const double maxBin = (s_idx != 0x7fffffff) ? __longlong_as_double((long long)s_max) : 0.0;
+        const int binPos = (s_idx != 0x7fffffff) ? s_idx : -1;
+        if (st.centreBin < 0) st.centreBin = 0;                                        // :444-445
+        if (st.centreBin > end - 1) st.centreBin = end - 1;
+        // avePsd[] is zero outside the scanned range
+        const double aveC = (st.centreBin >= beg + 75 && st.centreBin < end - 75) ? boxcar(st.centreBin) : 0.0;
+        const double PSD_AVE = (double)(2.0f / (10 + 1)), PSD_INV = (double)(1.0f - (2.0f / (10 + 1)));   // :401-402
+        const double CF_AVE = (double)(2.0f / (1 + 1)), CF_INV = (double)(1.0f - (2.0f / (1 + 1)));       // :399-400
+        st.avePeakPower = __dadd_rn(__dmul_rn(PSD_AVE, aveC), __dmul_rn(PSD_INV, st.avePeakPower));       // :446
+        if (maxBin > __dmul_rn(__ddiv_rn(st.avePeakPower, 4.0), 5.0) && binPos > 0) {                     // :447
+            st.aveCentreBin = __dadd_rn(__dmul_rn(CF_AVE, (double)(float)binPos), __dmul_rn(CF_INV, st.aveCentreBin));
+            const double c = __dadd_rn(st.aveCentreBin, 1.0);
+            st.centreBin = (c != c) ? 0 : (c >= 2147483647.0 ? 2147483647 : (c <= -2147483648.0 ? (int)0x80000000 : (int)c));
+        }
+        if (st.centreBin < 102) st.centreBin = 102;                                    // :453
+        state[ch] = st;
+        s_centre = st.centreBin;
+    }
+    __syncthreads();
+    const int c0 = s_centre - 102;                                                     // :458
+    if (tid < 204) {
+        const int k = c0 + tid;
+        rev[(size_t)ch * N + tid] = (k >= 0 && k < N) ? x[k] : make_double2(0.0, 0.0);
+    }
+}
+
+// :461-463 RxDownSample(re, re) on the inverse transform's real part (scaled by 1/N as
+// complexInverse(.., true) does), decimator FIR in the reference order; one thread per output.
+__global__ void __launch_bounds__(128) k_at_decim(const double2 *__restrict__ inv, int N, double inv_scale,
+                                                  const double2 *__restrict__ hist_in, double2 *__restrict__ hist_out,
+                                                  const double *__restrict__ taps, int ntaps, int D, int n0, int NO,
+                                                  double2 *__restrict__ ds_out, int max_ds)
+{
+    const int ch = blockIdx.y;
+    const int H = ntaps - 1;
+    const double2 *x = inv + (size_t)ch * N;
+    auto sample = [&](int n) {                         // local sample n (negative: previous block)
+        if (n < 0) {
+            const int k = n + H;
+            return (k >= 0) ? hist_in[(size_t)ch * kMaxDsTaps + k].x : 0.0;
+        }
+        return __dmul_rn(x[n].x, inv_scale);
+    };
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < NO) {
+        const int n = n0 + m * D;
+        double a = 0.0;
+        for (int k = 0; k < ntaps; k++) a = __dadd_rn(a, __dmul_rn(sample(n - k), taps[k]));   // :479-483
+        const double o = __dmul_rn(a, 0.9 * 32768.0);                                          // :486
+        ds_out[(size_t)ch * max_ds + m] = make_double2(o, o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < H) {          // new history: the last H inputs
+        const int n = N - H + threadIdx.x;
+        const double v = sample(n);
+        hist_out[(size_t)ch * kMaxDsTaps + threadIdx.x] = make_double2(v, v);
+    }
+}
+
 // ------------------------------------------------------------------ matched filter
 struct DmParams {
     const double2 *ds;         // [nchan][max_ds]
@@ -735,6 +854,50 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     return f32 ? launch_stream_shape<stream::PREC_F32, 64, 20>(b, sp) : launch_stream_shape<stream::PREC_F64, 64, 20>(b, sp);
 }
 
+// doBufferFFT (:406-464) for every channel of the bank: binary64 forward transform, search,
+// 204 bins to DC, inverse transform, decimator on the real part.  The tuner phase is not
+// advanced (the reference's FFT variant never calls RxMixTuner).
+template <int FMT>
+int autotune_block(jsdr_bpsk *b, const void *d_in, int S, long long chan_stride, int ic, int qc, int n0, int NO)
+{
+    jsdr_ctx *ctx = b->ctx;
+    const int nchan = b->nchan, N = S;
+    const size_t bytes = sizeof(double2) * (size_t)nchan * (size_t)N;
+    if (!b->d_at_state) {
+        void **bufs[] = {(void **)&b->d_at_work[0], (void **)&b->d_at_work[1], (void **)&b->d_at_rev[0], (void **)&b->d_at_rev[1]};
+        for (void **pp : bufs) {
+            cudaError_t e = cudaMalloc(pp, bytes);
+            if (e != cudaSuccess) {
+                set_error("auto-tune workspace: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+                cudaGetLastError();
+                return JSDR_ENOMEM;
+            }
+        }
+        JSDR_CUDA(cudaMalloc((void **)&b->d_at_state, sizeof(AutoTuneState) * (size_t)nchan));
+        JSDR_CUDA(cudaMemsetAsync(b->d_at_state, 0, sizeof(AutoTuneState) * (size_t)nchan, ctx->stream));
+    }
+    JSDR_REQUIRE(fftg::make_plan(N).nstages > 0, JSDR_EUNSUPPORTED, "block length has a prime factor other than 2, 3, 5, 7");
+    JSDR_REQUIRE(N >= 1024, JSDR_EUNSUPPORTED, "auto-tune needs blocks of at least 1024 samples");
+    const long long total = (long long)nchan * N;
+    k_at_load<FMT><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in, chan_stride, S, nchan, ic, qc, b->d_at_work[0]);
+    JSDR_TRY(launched(ctx, "k_at_load"));
+    int rc = JSDR_OK;
+    double2 *fwd = fftg::run<double>(ctx, ctx->stream, b->d_at_work[0], b->d_at_work[1], N, nchan, -1, &rc);   // :422-423
+    if (rc != JSDR_OK) return rc;
+    JSDR_CUDA(cudaMemsetAsync(b->d_at_rev[0], 0, bytes, ctx->stream));                                         // :419-420
+    const size_t smem = sizeof(double) * (size_t)(N / 4 + 64);
+    JSDR_CUDA(cudaFuncSetAttribute(k_at_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_at_search<<<nchan, 256, smem, ctx->stream>>>(fwd, b->d_at_rev[0], N, b->doUp, b->d_at_state);
+    JSDR_TRY(launched(ctx, "k_at_search"));
+    double2 *inv = fftg::run<double>(ctx, ctx->stream, b->d_at_rev[0], b->d_at_rev[1], N, nchan, +1, &rc);     // :459
+    if (rc != JSDR_OK) return rc;
+    dim3 grid((std::max(NO, 1) + 127) / 128, nchan);
+    k_at_decim<<<grid, 128, 0, ctx->stream>>>(inv, N, 1.0 / (double)N, b->d_ds_hist[b->ds_hist_cur],
+                                              b->d_ds_hist[b->ds_hist_cur ^ 1], b->d_taps, b->ntaps, b->D, n0, NO,
+                                              b->d_ds_out, b->max_ds);
+    return launched(ctx, "k_at_decim");
+}
+
 // `after_input` (optional) is called once the input is on the device and before
 // the main stream waits for the scouts: the pump enqueues the FFT there, so the
 // data-independent phase replay hides behind it.
@@ -764,9 +927,11 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     // ---- fork: data-independent work on the side stream.  The tuner plan for this
     // block was normally computed while the previous block was being processed.
     jsdr_bpsk::TunerPlan &P = b->plan[b->plan_cur];
+    const bool autotune = b->dofft != 0;               // :358-364 receive(): doBufferFFT instead of doBufferTune
+    if (autotune) JSDR_REQUIRE(S == b->max_block, JSDR_EINVAL, "auto-tune needs whole blocks of max_block_samples");
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    if (!(P.valid && P.S == S)) JSDR_TRY(launch_scout(b, P, S));
+    if (!autotune && !(P.valid && P.S == S)) JSDR_TRY(launch_scout(b, P, S));
     if (b->stages >= 2 && NO > 0) {
         const double vco_inc = 2.0 * M_PI * 1200.0 / (double)9600;      // :88
         const double bit_inc = 1.0 / (double)9600, bit_time = 1.0 / (double)1200;   // :91-92
@@ -791,8 +956,11 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         d_in = b->d_in;
     }
     if (after_input) JSDR_TRY(after_input(user, d_in));
-    JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ready, 0));
+    if (!autotune) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ready, 0));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (autotune) {
+        JSDR_TRY(autotune_block<FMT>(b, d_in, S, chan_stride, ic, qc, n0, NO));
+    } else {
 
     // ---- tuner + decimator
     MixParams mp;
@@ -868,6 +1036,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         if (Pn.used) JSDR_CUDA(cudaStreamWaitEvent(ctx->side, Pn.consumed, 0));
         JSDR_TRY(launch_scout(b, Pn, S));
     }
+    }   // !autotune
     b->ds_hist_cur ^= 1;
     b->ds_cnt = (b->ds_cnt + S) % D;
     b->cnt_raw += S;
@@ -1024,7 +1193,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
                     b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix,
                     b->d_bit_roll, b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_out, b->d_ts, b->d_bits,
-                    b->d_bit_at, b->d_nbits, b->d_in};
+                    b->d_bit_at, b->d_nbits, b->d_in, b->d_at_work[0], b->d_at_work[1], b->d_at_rev[0], b->d_at_rev[1], b->d_at_state};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 2; i++) {
         if (b->plan[i].ready) cudaEventDestroy(b->plan[i].ready);
@@ -1038,6 +1207,28 @@ extern "C" int jsdr_bpsk_set_stages(jsdr_bpsk *b, int stages)
 {
     JSDR_REQUIRE(b && stages >= 1 && stages <= 3, JSDR_EINVAL, "stages must be 1..3");
     b->stages = stages;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_bpsk_set_autotune(jsdr_bpsk *b, int dofft, int do_upper)
+{
+    JSDR_REQUIRE(b, JSDR_EINVAL, "null argument");
+    b->dofft = dofft != 0;
+    b->doUp = do_upper != 0;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_bpsk_read_centre(jsdr_bpsk *b, int32_t *centre_bin)
+{
+    JSDR_REQUIRE(b && centre_bin, JSDR_EINVAL, "null argument");
+    jsdr_ctx *ctx = b->ctx;
+    JSDR_TRY(ctx->bind());
+    for (int c = 0; c < b->nchan; c++) centre_bin[c] = 0;
+    if (!b->d_at_state) return JSDR_OK;                // no auto-tune block yet (centreBin = 0, :405)
+    std::vector<AutoTuneState> st(b->nchan);
+    JSDR_CUDA(cudaMemcpyAsync(st.data(), b->d_at_state, sizeof(AutoTuneState) * (size_t)b->nchan, cudaMemcpyDeviceToHost, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < b->nchan; c++) centre_bin[c] = st[c].centreBin;
     return JSDR_OK;
 }
 

@@ -3,6 +3,7 @@
 
 #include <vector>
 
+#include "fft_generic.cuh"
 #include "fft_kernels.cuh"
 #include "fft_plans.h"
 #include "handles.h"
@@ -31,6 +32,97 @@ static const PlanEntry *find_plan(int n)
     return nullptr;
 }
 
+
+// ---- lengths without a single-CTA plan: fft_generic.cuh stages + a PSD pass -------------
+__global__ void __launch_bounds__(256) k_generic_load(const void *__restrict__ in, float2 *__restrict__ out, long long total,
+                                                     int in_fmt, int ic, int qc)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    if (in_fmt == IN_F32) {
+        out[i] = reinterpret_cast<const float2 *>(in)[i];
+    } else {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(in)[i];
+        // JavaAudio.java:281-288: s += (short)ic with 16-bit wrap; the 1/32767 is folded into cf
+        const short si = (short)((int)(w & 0xffffu) + ic), sq = (short)((int)(w >> 16) + qc);
+        out[i] = make_float2((float)si, (float)sq);
+    }
+}
+
+// fft.java:199-224 on a finished spectrum: one CTA per block
+__global__ void __launch_bounds__(256) k_generic_psd(const float2 *__restrict__ spec, float *__restrict__ out,
+                                                    int32_t *__restrict__ peak_bin, int N, int rate, float cf)
+{
+    __shared__ unsigned s_max;
+    __shared__ int s_idx;
+    const long blk = blockIdx.x;
+    const float2 *x = spec + blk * (long)N;
+    float *psd = out + blk * (long)(N + 2);
+    if (threadIdx.x == 0) {
+        s_max = 0u;
+        s_idx = 0x7fffffff;
+    }
+    __syncthreads();
+    float best = -3.4028234663852886e38f;
+    int best_idx = 0x7fffffff;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const float2 v = x[k];
+        const float pw = __fmul_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), cf);
+        const float db = 3.0102999566398120f * lg2_approx(pw);
+        psd[k] = db;
+        if (best < db) {           // k increases per thread: the first maximum wins
+            best = db;
+            best_idx = k;
+        }
+    }
+    const unsigned key = (best_idx == 0x7fffffff) ? 0u : ordered_key(best);
+    if (key != 0u) atomicMax(&s_max, key);
+    __syncthreads();
+    if (key != 0u && key == s_max) atomicMin(&s_idx, best_idx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned k = s_max;
+        const int bin = (k != 0u) ? s_idx : -1;
+        float m = -3.4028234663852886e38f;
+        if (k != 0u) m = __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+        int p = (bin < 0) ? -1 : 2 * bin;              // fft.java:214-221, int32 wrap, truncating division
+        const int datlen = 2 * N;
+        if (p >= datlen / 2) p -= datlen;
+        p = (int)((unsigned)p * (unsigned)rate) / datlen;
+        psd[N] = (float)p;
+        psd[N + 1] = m;
+        if (peak_bin) peak_bin[blk] = bin;
+    }
+}
+
+static int launch_generic(jsdr_fft *f, const Args &a, int in_fmt, int out_mode, cudaStream_t st)
+{
+    jsdr_ctx *ctx = f->ctx;
+    const size_t need = (size_t)f->max_batch * (size_t)f->n * sizeof(float2);
+    if (!f->d_work[0]) {
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMalloc(&f->d_work[i], need);
+            if (e != cudaSuccess) {
+                set_error("fft workspace: cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+                cudaGetLastError();
+                return JSDR_ENOMEM;
+            }
+        }
+    }
+    const long long total = (long long)a.nblocks * f->n;
+    k_generic_load<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.in, f->d_work[0], total, in_fmt, a.ic, a.qc);
+    JSDR_TRY(launched(ctx, "k_generic_load"));
+    int rc = JSDR_OK;
+    float2 *res = fftg::run<float>(ctx, st, f->d_work[0], f->d_work[1], f->n, a.nblocks, -1, &rc);
+    if (rc != JSDR_OK) return rc;
+    if (out_mode == OUT_SPECTRUM) {
+        JSDR_CUDA(cudaMemcpyAsync(a.out, res, (size_t)total * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        return JSDR_OK;
+    }
+    k_generic_psd<<<a.nblocks, 256, 0, st>>>(res, a.out, a.peak_bin, f->n, a.rate, a.cf);
+    return launched(ctx, "k_generic_psd");
+}
+
 int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, int32_t *d_peak,
            int out_mode, int ic, int qc, cudaStream_t st)
 {
@@ -52,6 +144,7 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
     a.cf = cf;
     a.ic = ic;
     a.qc = qc;
+    if (!f->launch) return launch_generic(f, a, in_fmt, out_mode, st);
     return reinterpret_cast<launch_fn>(f->launch)(f->ctx, a, in_fmt, out_mode, st);
 }
 
@@ -60,15 +153,19 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
 
 using namespace jsdr;
 
-extern "C" int jsdr_fft_supported(int n) { return fft::find_plan(n) != nullptr; }
+extern "C" int jsdr_fft_supported(int n)
+{
+    if (fft::find_plan(n)) return 1;                       // single-CTA plan
+    return n >= 2 && fftg::make_plan(n).nstages > 0 ? 2 : 0;   // staged path (slower)
+}
 
 extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, jsdr_fft **out)
 {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(max_batch > 0 && rate > 0, JSDR_EINVAL, "max_batch and rate must be positive");
     const fft::PlanEntry *p = fft::find_plan(n);
-    if (!p) {
-        set_error("jsdr_fft_create: no FFT plan for n=%d", n);
+    if (!p && !(n >= 2 && fftg::make_plan(n).nstages > 0)) {
+        set_error("jsdr_fft_create: no FFT plan for n=%d (needs n = 2^a 3^b 5^c 7^d)", n);
         return JSDR_EUNSUPPORTED;
     }
     JSDR_TRY(ctx->bind());
@@ -77,7 +174,7 @@ extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, js
     f->n = n;
     f->rate = rate;
     f->max_batch = max_batch;
-    f->launch = reinterpret_cast<void *>(p->fn);
+    f->launch = p ? reinterpret_cast<void *>(p->fn) : nullptr;   // null: the staged path
     // twiddle table exp(-2*pi*i*t/n), computed in double, rounded once
     std::vector<float2> tw(n);
     for (int t = 0; t < n; t++) {
@@ -110,6 +207,8 @@ extern "C" int jsdr_fft_destroy(jsdr_fft *f)
     cudaFree(f->d_in);
     cudaFree(f->d_out);
     cudaFree(f->d_peak);
+    cudaFree(f->d_work[0]);
+    cudaFree(f->d_work[1]);
     delete f;
     return JSDR_OK;
 }

@@ -13,6 +13,7 @@ struct jsdr_fft {
     int n = 0, rate = 0, max_batch = 0;
     void *launch = nullptr;          // jsdr::fft::launch_fn of the plan
     float2 *d_tw = nullptr;          // exp(-2*pi*i*t/n)
+    float2 *d_work[2] = {nullptr, nullptr};   // ping-pong workspace of the staged path (no single-CTA plan)
     // staging for host-pointer calls (allocated on first use)
     void *d_in = nullptr;
     float *d_out = nullptr;
@@ -30,6 +31,12 @@ struct TimingState {
     double lastI, lastQ;
     int bitPos, peakPos, newPeak, pad;
     long long cntBit;
+};
+
+// per-channel state of the auto-tune search (FUNcubeBPSKDemod.java:403-405)
+struct AutoTuneState {
+    double avePeakPower, aveCentreBin;
+    int centreBin, pad;
 };
 
 constexpr int kMaxDsTaps = 128;
@@ -90,6 +97,12 @@ struct jsdr_bpsk {
 
     void *d_in = nullptr;            // staging for host-pointer calls
     size_t in_cap = 0;
+
+    // auto-tune variant (doBufferFFT, FUNcubeBPSKDemod.java:406-464)
+    int dofft = 0, doUp = 0;
+    double2 *d_at_work[2] = {nullptr, nullptr};   // [nchan][max_block] forward transform ping-pong
+    double2 *d_at_rev[2] = {nullptr, nullptr};    // [nchan][max_block] 204 bins at DC, inverse ping-pong
+    jsdr::bpsk::AutoTuneState *d_at_state = nullptr;   // [nchan]
 };
 
 struct jsdr_demod {

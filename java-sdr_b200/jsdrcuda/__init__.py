@@ -82,6 +82,8 @@ _SIGS = {
     "jsdr_bpsk_destroy": [_vp],
     "jsdr_bpsk_set_stages": [_vp, _i],
     "jsdr_bpsk_set_tuning": [_vp, _i, _d],
+    "jsdr_bpsk_set_autotune": [_vp, _i, _i],
+    "jsdr_bpsk_read_centre": [_vp, _vp],
     "jsdr_bpsk_set_precision": [_vp, _i],
     "jsdr_bpsk_set_kernel": [_vp, _i],
     "jsdr_bpsk_set_ds_filter": [_vp, _vp, _i],
@@ -389,6 +391,16 @@ class FUNcubeBPSKDemod:
         _ck(lib().jsdr_bpsk_set_tuning(self.h, chan, hz))
         self.tuning[chan] = hz
 
+    def set_autotune(self, dofft: bool, upper: bool = False):
+        """doBufferFFT instead of doBufferTune (config "FUNcube<i>-bpsk-dofft" / "-upper")."""
+        self.dofft = bool(dofft)
+        _ck(lib().jsdr_bpsk_set_autotune(self.h, int(dofft), int(upper)))
+
+    def centre_bins(self) -> np.ndarray:
+        out = np.zeros(self.nchan, dtype=np.int32)
+        _ck(lib().jsdr_bpsk_read_centre(self.h, _ptr(out)))
+        return out
+
     def set_precision(self, precision: int):
         _ck(lib().jsdr_bpsk_set_precision(self.h, precision))
 
@@ -426,7 +438,14 @@ class FUNcubeBPSKDemod:
             _ck(lib().jsdr_bpsk_receive_f32(self.h, _ptr(d_in), S, chan_stride, MEM_DEVICE))
 
     def _published(self):
-        if self.publish is not None:                          # :377-378
+        if self.publish is None:
+            return
+        if getattr(self, "dofft", False):                     # :455-456
+            centre = self.centre_bins()
+            for c in range(self.nchan):
+                self.publish.setPublish(f"{self.name}{c}-bpsk-tune", -1)
+                self.publish.setPublish(f"{self.name}{c}-bpsk-centre", int(centre[c]))
+        else:                                                 # :377-378
             for c in range(self.nchan):
                 self.publish.setPublish(f"{self.name}{c}-bpsk-centre", -1)
                 self.publish.setPublish(f"{self.name}{c}-bpsk-tune", int(self.tuning[c]))
