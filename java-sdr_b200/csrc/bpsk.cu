@@ -636,58 +636,111 @@ struct TimingParams {
     long long cnt_ds0;
 };
 
-__global__ void __launch_bounds__(128) k_timing(const TimingParams p)
+constexpr int kTimingTile = 32;      // 9600 S/s samples staged per channel per step
+
+// :533-595, one lane per channel, one warp per CTA (the recurrence is latency bound, so the
+// warps are spread over as many SMs as there are).  The matched-filter output is staged through
+// shared memory in [32 channels][32 samples] tiles — one coalesced 512-byte row per warp
+// instruction, loaded one tile ahead — and each lane then walks its own row.
+__global__ void __launch_bounds__(32) k_timing(const TimingParams p)
 {
-    // :533-595, one thread per channel; dmEnergy[] lives in shared memory because it
-    // is indexed by the running bit position
-    __shared__ double sE[8][128];
-    const int tid = threadIdx.x;
-    const int ch = blockIdx.x * 128 + tid;
-    if (ch >= p.nchan) return;
+    __shared__ double sE[8][32];                       // dmEnergy[], indexed by the running bit position
+    __shared__ double2 sDm[2][32][kTimingTile + 1];    // odd pitch in 16-byte units: row-per-lane reads do not conflict
+    const int lane = threadIdx.x;
+    const int ch0 = blockIdx.x * 32;
+    const int ch = min(ch0 + lane, p.nchan - 1);
+    const bool live = ch0 + lane < p.nchan;
+    const int rows = min(32, p.nchan - ch0);
     TimingState st = p.ts[ch];
 #pragma unroll
-    for (int i = 0; i < 8; i++) sE[i][tid] = st.dmEnergy[i];
+    for (int i = 0; i < 8; i++) sE[i][lane] = st.dmEnergy[i];
     const double S1 = 1.0 / 200.0, S2 = 1.0 / 800.0;
     const double C1 = 1.0 - S1, C2 = 1.0 - S2;
     double eOut = st.dmEnergyOut, lastI = st.lastI, lastQ = st.lastQ;
     int bitPos = st.bitPos, peakPos = st.peakPos, newPeak = st.newPeak;
     int nb = 0;
-    const double2 *dm = p.dm + (size_t)ch * p.max_ds;
     int8_t *bits = p.bits + (size_t)ch * p.max_bits;
     long long *bit_at = p.bit_at + (size_t)ch * p.max_bits;
-    for (int m = 0; m < p.NO; m++) {
-        double2 f = dm[m];
-        double energy1 = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));            // :534
-        sE[bitPos][tid] = __dadd_rn(__dmul_rn(sE[bitPos][tid], C1), __dmul_rn(energy1, S1));   // :535
-        if (bitPos == peakPos) {                                                       // :537
-            eOut = __dadd_rn(__dmul_rn(eOut, C2), __dmul_rn(energy1, S2));
-            double di = -__dadd_rn(__dmul_rn(lastI, f.x), __dmul_rn(lastQ, f.y));      // :539
-            double dq = __dadd_rn(__dmul_rn(lastI, f.y), -__dmul_rn(lastQ, f.x));      // :540
-            lastI = f.x;
-            lastQ = f.y;
-            double energy2 = __dsqrt_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dq, dq)));
-            if (energy2 > 100.0) {                                                     // :544
-                if (nb < p.max_bits) {
-                    bits[nb] = (di < 0.0) ? 1 : -1;                                    // :545,554
-                    bit_at[nb] = p.cnt_ds0 + m;
-                }
-                nb++;
-            }
-        }
-        if (bitPos == ((peakPos + 4) & 7)) peakPos = newPeak;      // :577 dmHalfTable = {4,5,6,7,0,1,2,3}
-        bitPos = (bitPos + 1) & 7;                                 // :579
-        if (p.bit_roll[m]) {                                       // :582-592
-            bitPos = 0;
-            double eMax = -1.0e10;                                 // (double)-1.0e10F, exact
+
+    const int ntiles = (p.NO + kTimingTile - 1) / kTimingTile;
+    double2 pre[32];                                   // next tile: row r, this lane's sample
+    auto load_tile = [&](int t) {
+        const int m = t * kTimingTile + lane;
 #pragma unroll
-            for (int n = 0; n < 8; n++) {
-                double e = sE[n][tid];
-                if (e > eMax) { newPeak = n; eMax = e; }
+        for (int r = 0; r < 32; r++) {
+            pre[r] = make_double2(0.0, 0.0);
+            if (r < rows && m < p.NO) pre[r] = p.dm[(size_t)(ch0 + r) * p.max_ds + m];
+        }
+    };
+    auto store_tile = [&](int t) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) sDm[t & 1][r][lane] = pre[r];
+    };
+    if (ntiles > 0) load_tile(0);
+    for (int t = 0; t < ntiles; t++) {
+        __syncwarp();
+        store_tile(t);
+        if (t + 1 < ntiles) load_tile(t + 1);
+        __syncwarp();
+        const int cnt = min(kTimingTile, p.NO - t * kTimingTile);
+        // bit-phase roll-overs of this tile (the same for every channel): one bit per sample
+        const int mr = t * kTimingTile + lane;
+        const unsigned rollmask = __ballot_sync(0xffffffffu, mr < p.NO && p.bit_roll[mr] != 0);
+        // Decisions of different channels fall on different samples (bitPos == peakPos), and two
+        // decisions of one channel are at least 5 samples apart.  The per-sample part therefore
+        // only notes the decision sample; the expensive part (:538-574) runs for all lanes
+        // together once every 4 samples instead of diverging on every sample.
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            bool pend = false;
+            double2 pf = make_double2(0.0, 0.0);
+            double pe1 = 0.0;
+            int pm = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                if (j < cnt) {
+                    const double2 f = sDm[t & 1][lane][j];
+                    const double energy1 = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));            // :534
+                    sE[bitPos][lane] = __dadd_rn(__dmul_rn(sE[bitPos][lane], C1), __dmul_rn(energy1, S1));   // :535
+                    if (bitPos == peakPos) {                                                               // :537
+                        pend = true;
+                        pf = f;
+                        pe1 = energy1;
+                        pm = t * kTimingTile + j;
+                    }
+                    if (bitPos == ((peakPos + 4) & 7)) peakPos = newPeak;      // :577 dmHalfTable = {4,5,6,7,0,1,2,3}
+                    bitPos = (bitPos + 1) & 7;                                 // :579
+                    if ((rollmask >> j) & 1u) {                                // :582-592 (same for every channel)
+                        bitPos = 0;
+                        double eMax = -1.0e10;                                 // (double)-1.0e10F, exact
+#pragma unroll
+                        for (int n = 0; n < 8; n++) {
+                            double e = sE[n][lane];
+                            if (e > eMax) { newPeak = n; eMax = e; }
+                        }
+                    }
+                }
+            }
+            if (pend) {
+                eOut = __dadd_rn(__dmul_rn(eOut, C2), __dmul_rn(pe1, S2));                 // :538
+                double di = -__dadd_rn(__dmul_rn(lastI, pf.x), __dmul_rn(lastQ, pf.y));    // :539
+                double dq = __dadd_rn(__dmul_rn(lastI, pf.y), -__dmul_rn(lastQ, pf.x));    // :540
+                lastI = pf.x;
+                lastQ = pf.y;
+                double energy2 = __dsqrt_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dq, dq)));
+                if (energy2 > 100.0) {                                                     // :544
+                    if (nb < p.max_bits && live) {
+                        bits[nb] = (di < 0.0) ? 1 : -1;                                    // :545,554
+                        bit_at[nb] = p.cnt_ds0 + pm;
+                    }
+                    nb++;
+                }
             }
         }
     }
+    if (!live) return;
 #pragma unroll
-    for (int i = 0; i < 8; i++) st.dmEnergy[i] = sE[i][tid];
+    for (int i = 0; i < 8; i++) st.dmEnergy[i] = sE[i][lane];
     st.dmEnergyOut = eOut;
     st.lastI = lastI;
     st.lastQ = lastQ;
@@ -1078,7 +1131,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
             tp.max_bits = b->max_bits;
             tp.cnt_ds0 = b->cnt_ds;
             ProfScope prof(ctx, JSDR_K_TIMING, ctx->stream);
-            k_timing<<<(nchan + 127) / 128, 128, 0, ctx->stream>>>(tp);
+            k_timing<<<(nchan + 31) / 32, 32, 0, ctx->stream>>>(tp);
             JSDR_TRY(launched(ctx, "k_timing"));
         }
     }

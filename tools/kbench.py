@@ -77,10 +77,34 @@ def fft(ns, total=1 << 28):
     ctx.close()
 
 
+def chain(nchan=4096, S=131072, rate=192000):
+    """Full FUNcube chain (tuner, 27-tap decimator, matched filter, bit timing) per stage count."""
+    ctx = J.Context(0)
+    rng = np.random.default_rng(1)
+    tun = rng.uniform(2000, 90000, nchan)
+    d_raw = ctx.dev_alloc(nchan * S * 4)
+    tile = rng.integers(-20000, 20000, (64, 2 * S)).astype(np.int16)
+    for c0 in range(0, nchan, 64):
+        d_raw.upload(tile[: min(64, nchan - c0)], offset=c0 * S * 4)
+    for stages in (1, 2, 3):
+        bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate), tuning=tun, max_block=S, stages=stages)
+        ctx.profile(True)
+        ms = time_ms(ctx, lambda: bank.receive_dev(d_raw, S, S, s16=True))
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        per = {k: round(v[0] / max(v[1], 1), 3) for k, v in prof.items() if v[1]}
+        print(f"chain stages={stages} nchan={nchan} S={S}: {ms:8.3f} ms  {nchan * S / ms / 1e3:9.1f} Msamples/s  per-kernel ms {per}", flush=True)
+        bank.close()
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mix"
     if what == "mix":
         a = [int(x) for x in sys.argv[2:]]
         mix(*a)
+    elif what == "chain":
+        chain(*[int(x) for x in sys.argv[2:]])
     else:
         fft([int(x) for x in sys.argv[2:]] or [256, 1024, 4096, 9600, 16384, 19200])
+
