@@ -851,7 +851,7 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
     jsdr_ctx *ctx = b->ctx;
     constexpr int W = stream::kWarps;
     auto kern = stream::k_mixdecim_stream<PREC, NTAPS, DD, W>;
-    constexpr size_t smem = stream::smem_bytes<W>();
+    constexpr size_t smem = stream::smem_bytes<W, DD>();
     static bool attr_done = false;
     if (!attr_done) {
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

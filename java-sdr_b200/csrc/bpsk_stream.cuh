@@ -110,14 +110,17 @@ struct Acc<PREC_F32> {
 };
 
 constexpr int kRing = 64;                 // samples per row in the ring: two 32-sample chunks
-constexpr int kPitch = kRing + 1;         // odd pitch (words): row-per-lane reads never conflict
+// The first D (rounded up to 4) positions of the ring are mirrored behind its end, so that a
+// period that would wrap can be read at fixed offsets below position p+64 instead.
+template <int DD> __host__ __device__ constexpr int mirror_len() { return (DD + 3) & ~3; }
+template <int DD> __host__ __device__ constexpr int row_pitch() { return (kRing + mirror_len<DD>()) | 1; }   // odd (words): no bank conflicts
 constexpr int kScratch = 24;              // uint16 per lane for the exact-replay path (>= D)
 constexpr int kTabBytes = 257 * 128;      // 8 x double2 or 16 x float2 copies of each of the 257 entries
 
-template <int W>
+template <int W, int DD>
 constexpr size_t smem_bytes()
 {
-    return (size_t)kTabBytes + (size_t)W * (32 * kPitch * 4 + 32 * kScratch * 2);
+    return (size_t)kTabBytes + (size_t)W * (32 * row_pitch<DD>() * 4 + 32 * kScratch * 2);
 }
 
 __device__ __forceinline__ double2 lds_d2(unsigned addr)
@@ -144,7 +147,8 @@ __device__ __forceinline__ void period_body(const Params &p, const uint32_t *myr
 {
     constexpr int NQ = (NTAPS + DD - 1) / DD;
     constexpr int H = NTAPS - 1;
-    const uint32_t *top = myrow + (s_hi & (kRing - 1));
+    const int ptop = s_hi & (kRing - 1);
+    const uint32_t *top = myrow + (ptop >= DD - 1 ? ptop : ptop + kRing);   // wrapping periods read the mirror
 #pragma unroll
     for (int j = 0; j < DD; j++) {
         const int s = s_hi - j;
@@ -210,6 +214,8 @@ template <int PREC, int NTAPS, int DD, int W>
 __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
 {
     constexpr int NQ = (NTAPS + DD - 1) / DD;          // live outputs per sample
+    constexpr int kPitch = row_pitch<DD>();
+    constexpr int MIR = mirror_len<DD>();
     constexpr int WARP_BYTES = 32 * kPitch * 4 + 32 * kScratch * 2;
     static_assert(DD <= kScratch && DD <= 32, "period");
     static_assert(NTAPS <= kMaxTaps && NQ <= 4, "taps");
@@ -290,6 +296,12 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
                 dst[1] = pre[i].y;
                 dst[2] = pre[i].z;
                 dst[3] = pre[i].w;
+                if ((c & 1) == 0 && spiece * 4 < MIR) {        // mirror of ring positions 0 .. MIR-1
+                    dst[kRing + 0] = pre[i].x;
+                    dst[kRing + 1] = pre[i].y;
+                    dst[kRing + 2] = pre[i].z;
+                    dst[kRing + 3] = pre[i].w;
+                }
                 dst += 4 * kPitch;
             }
         };
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
             }
 
             // ---- convert, mix, accumulate
-            if (s_lo >= 0 && (s_hi & (kRing - 1)) >= DD - 1 && !iqcorr) period_body<PREC, NTAPS, DD, true>(p, myrow, taddr, s_hi, ch, acc);
+            if (s_lo >= 0 && !iqcorr) period_body<PREC, NTAPS, DD, true>(p, myrow, taddr, s_hi, ch, acc);
             else period_body<PREC, NTAPS, DD, false>(p, myrow, taddr, s_hi, ch, acc);
 
             // ---- the oldest role is complete: scale (:469,486), store, rotate
