@@ -187,6 +187,25 @@ int jsdr_demod_set_flags(jsdr_demod *d, int dofir, int dodwn);
 int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int nsamples, int64_t chan_stride,
                            float *out /* nchan*2*nsamples */, int mem);
 
+/* The detectors, AGC and s16 narrowing that follow the FIR + NCO in demod.receive
+ * (demod.java:405-481): mode 0 off, 1 raw (I), 2 AM (envelope minus its running mean),
+ * 3 NFM / 4 WFM (quadrature discriminator, gain rate/5000 or rate/75000); doagc scales
+ * by 1.0f/max.  audio is what receive() writes to bbf: one s16 per input sample
+ * (the reference writes it to both stereo channels, :474-477), nchan*nsamples;
+ * max_avg (nullable) returns max and avg per channel (painted at :544-547). */
+int jsdr_demod_set_mode(jsdr_demod *d, int mode, int doagc);
+int jsdr_demod_receive_audio_f32(jsdr_demod *d, const float *iq, int nsamples, int64_t chan_stride,
+                                 int16_t *audio, float *max_avg /* nchan*2 */, int mem);
+
+/* -------------------------------------------------------------- waterfall.java
+ * paintLine (waterfall.java:90-107) for `rows` published "fft-psd" rows (float[n+2]
+ * each): max-decimate to `width` pixels, -100..0 dBFS -> 0..255, tint with peak_rgb
+ * (waterfall.java:15, Color.CYAN = 0x00ffff), rotate by width/2, ARGB out
+ * [rows][width].  With JSDR_MEM_DEVICE it chains behind jsdr_fft_receive_* so that
+ * only the pixel row returns to the host. */
+int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int rows, int width, uint32_t peak_rgb,
+                        int32_t *pixels, int mem);
+
 /* ------------------------------------------------------------------ fir.java
  * The four arithmetic methods of the stand-alone fir.java tool:
  *   weights     :169-195  (host, one-off)            jsdr_fir_design

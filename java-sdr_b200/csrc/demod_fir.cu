@@ -240,6 +240,7 @@ extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_blo
     if (e == cudaSuccess) e = cudaMalloc(&d->d_chunk_car, sizeof(float) * nc * d->max_chunks);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_hist[0], sizeof(float2) * kHist * nc);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_hist[1], sizeof(float2) * kHist * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_lilq, sizeof(float2) * nc);
     if (e != cudaSuccess) {
         set_error("jsdr_demod_create: %s", cudaGetErrorString(e));
         jsdr_demod_destroy(d);
@@ -251,6 +252,7 @@ extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_blo
     cudaMemsetAsync(d->d_car, 0, sizeof(float) * nc, ctx->stream);
     cudaMemsetAsync(d->d_hist[0], 0, sizeof(float2) * kHist * nc, ctx->stream);
     cudaMemsetAsync(d->d_hist[1], 0, sizeof(float2) * kHist * nc, ctx->stream);
+    cudaMemsetAsync(d->d_lilq, 0, sizeof(float2) * nc, ctx->stream);
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = d;
     return JSDR_OK;
@@ -262,7 +264,8 @@ extern "C" int jsdr_demod_destroy(jsdr_demod *d)
     d->ctx->bind();
     cudaStreamSynchronize(d->ctx->side);
     cudaStreamSynchronize(d->ctx->stream);
-    void *ptrs[] = {d->d_w, d->d_phi, d->d_car, d->d_chunk_car, d->d_hist[0], d->d_hist[1], d->d_in, d->d_out};
+    void *ptrs[] = {d->d_w, d->d_phi, d->d_car, d->d_chunk_car, d->d_hist[0], d->d_hist[1], d->d_in, d->d_out,
+                    d->d_lilq, d->d_det, d->d_audio};
     for (void *p : ptrs) cudaFree(p);
     delete d;
     return JSDR_OK;
@@ -320,16 +323,13 @@ extern "C" int jsdr_demod_set_flags(jsdr_demod *d, int dofir, int dodwn)
     return JSDR_OK;
 }
 
-extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
-                                      float *out, int mem)
+namespace {
+
+// FIR + NCO of one block for every channel; the result stays on the device in *d_result
+// ([nchan][S] float2: `out` itself for device calls, the staging buffer for host calls).
+int demod_run(jsdr_demod *d, const float *iq, int S, int64_t chan_stride, float *out, int mem, float2 **d_result)
 {
-    JSDR_REQUIRE(d && iq && out, JSDR_EINVAL, "null argument");
-    JSDR_REQUIRE(S >= 0 && S <= d->max_block, JSDR_EINVAL, "nsamples exceeds max_block_samples");
-    JSDR_REQUIRE(chan_stride == 0 || chan_stride >= S, JSDR_EINVAL, "chan_stride smaller than nsamples");
-    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
-    if (S == 0) return JSDR_OK;
     jsdr_ctx *ctx = d->ctx;
-    JSDR_TRY(ctx->bind());
     const int nchan = d->nchan;
     if (d->dodwn) {
         JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -344,9 +344,11 @@ extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int
     if (mem == JSDR_MEM_HOST) {
         const size_t total = (chan_stride == 0) ? (size_t)S : (size_t)chan_stride * (nchan - 1) + S;
         JSDR_TRY(grow(&d->d_in, &d->in_cap, total * sizeof(float2)));
-        JSDR_TRY(grow(reinterpret_cast<void **>(&d->d_out), &d->out_cap, out_bytes));
         JSDR_CUDA(cudaMemcpyAsync(d->d_in, iq, total * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
         d_in = reinterpret_cast<const float2 *>(d->d_in);
+    }
+    if (mem == JSDR_MEM_HOST || !out) {
+        JSDR_TRY(grow(reinterpret_cast<void **>(&d->d_out), &d->out_cap, out_bytes));
         d_out = reinterpret_cast<float2 *>(d->d_out);
     }
     if (d->dodwn) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -371,8 +373,169 @@ extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int
         JSDR_TRY(launched(ctx, "k_demod_tail"));
         d->hist_cur ^= 1;
     }
+    *d_result = d_out;
+    return JSDR_OK;
+}
+
+int demod_check(jsdr_demod *d, const void *iq, const void *out, int S, int64_t chan_stride, int mem)
+{
+    JSDR_REQUIRE(d && iq && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(S >= 0 && S <= d->max_block, JSDR_EINVAL, "nsamples exceeds max_block_samples");
+    JSDR_REQUIRE(chan_stride == 0 || chan_stride >= S, JSDR_EINVAL, "chan_stride smaller than nsamples");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    return JSDR_OK;
+}
+
+}  // namespace
+
+extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
+                                      float *out, int mem)
+{
+    JSDR_TRY(demod_check(d, iq, out, S, chan_stride, mem));
+    if (S == 0) return JSDR_OK;
+    jsdr_ctx *ctx = d->ctx;
+    JSDR_TRY(ctx->bind());
+    float2 *res = nullptr;
+    JSDR_TRY(demod_run(d, iq, S, chan_stride, out, mem, &res));
     if (mem == JSDR_MEM_HOST) {
-        JSDR_CUDA(cudaMemcpyAsync(out, d->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        JSDR_CUDA(cudaMemcpyAsync(out, res, sizeof(float2) * (size_t)d->nchan * S, cudaMemcpyDeviceToHost, ctx->stream));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return JSDR_OK;
+}
+
+// ------------------------------------------------------------------ detectors, AGC, s16 (:405-481)
+namespace jsdr {
+namespace dsp {
+
+enum { MODE_OFF = 0, MODE_RAW = 1, MODE_AM = 2, MODE_NFM = 3, MODE_WFM = 4 };   // demod.java:39-43
+
+__device__ __forceinline__ int java_f2i(float x)
+{   // Java (int)float: NaN -> 0, saturating
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (int)0x80000000;
+    return (int)x;
+}
+
+// One CTA per channel.  Pass 1: the detector output of every sample (sample parallel; the FM
+// discriminator's previous sample is the neighbour, or the carried li/lq for the first) and the
+// block maximum of |.| (:448-463).  Pass 2 (AM): the running mean avg = ((k)*avg + x)/(k+1) is a
+// sequential float recurrence (:451), replayed by one thread over tiles staged in shared memory.
+// Pass 3: AM subtracts the mean, AGC scales by 1.0f/max, narrow to s16 as Java's (short) does
+// (:469-473).  `det` is scratch [nchan][S].
+__global__ void __launch_bounds__(256) k_detect(const float2 *__restrict__ mixed, int S, int mode, float fmgain, int doagc,
+                                                float2 *__restrict__ lilq, float *__restrict__ det,
+                                                int16_t *__restrict__ audio, float *__restrict__ max_avg)
+{
+    __shared__ unsigned s_max;
+    __shared__ int s_nan;
+    __shared__ float s_avg;
+    __shared__ float s_tile[2048];
+    const int ch = blockIdx.x, tid = threadIdx.x;
+    const float2 *x = mixed + (size_t)ch * S;
+    float *dv = det + (size_t)ch * S;
+    if (tid == 0) {
+        s_max = 0u;
+        s_nan = 0;
+        s_avg = 0.0f;
+    }
+    __syncthreads();
+    const float2 prev0 = lilq[ch];
+    unsigned mymax = 0u;
+    int mynan = 0;
+    for (int k = tid; k < S; k += blockDim.x) {
+        const float2 v = x[k];
+        float o;
+        if (mode == MODE_OFF) o = 0.0f;
+        else if (mode == MODE_RAW) o = v.x;
+        else if (mode == MODE_AM) {
+            // (float)Math.sqrt(sam[s]*sam[s]+sam[s+1]*sam[s+1]): float sum of squares, double sqrt
+            const float ss = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+            o = (float)__dsqrt_rn((double)ss);
+        } else {
+            const float2 l = (k == 0) ? prev0 : x[k - 1];          // li, lq (:456-458)
+            o = __fmul_rn(__fsub_rn(__fmul_rn(l.x, v.y), __fmul_rn(l.y, v.x)), fmgain);
+        }
+        dv[k] = o;
+        const float a = fabsf(o);
+        if (a != a) mynan = 1;
+        else mymax = max(mymax, __float_as_uint(a));               // non-negative floats order like their bits
+    }
+    atomicMax(&s_max, mymax);
+    if (mynan) s_nan = 1;
+    __syncthreads();
+    if ((mode == MODE_NFM || mode == MODE_WFM) && tid == 0 && S > 0) lilq[ch] = x[S - 1];
+    if (mode == MODE_AM) {
+        for (int t0 = 0; t0 < S; t0 += 2048) {
+            const int cnt = min(2048, S - t0);
+            for (int i = tid; i < cnt; i += blockDim.x) s_tile[i] = dv[t0 + i];
+            __syncthreads();
+            if (tid == 0) {
+                float avg = s_avg;
+                for (int i = 0; i < cnt; i++) {
+                    const int k = t0 + i;
+                    avg = __fdiv_rn(__fadd_rn(__fmul_rn((float)k, avg), s_tile[i]), (float)(k + 1));   // :451
+                }
+                s_avg = avg;
+            }
+            __syncthreads();
+        }
+    }
+    float mx = s_nan ? __uint_as_float(0x7fc00000u) : __uint_as_float(s_max);      // Math.max keeps NaN
+    const float avg = s_avg;
+    if (mode == MODE_AM) mx = __fsub_rn(mx, avg);                                  // :466-468
+    const float gain = doagc ? __fdiv_rn(1.0f, mx) : 1.0f;
+    for (int k = tid; k < S; k += blockDim.x) {
+        float o = dv[k];
+        if (mode == MODE_AM) o = __fsub_rn(o, avg);
+        o = __fmul_rn(o, gain);
+        audio[(size_t)ch * S + k] = (int16_t)(java_f2i(__fmul_rn(o, 32767.0f)) & 0xffff);   // (short)(float)
+    }
+    if (tid == 0 && max_avg) {
+        max_avg[2 * ch] = mx;
+        max_avg[2 * ch + 1] = avg;
+    }
+}
+
+}  // namespace dsp
+}  // namespace jsdr
+
+extern "C" int jsdr_demod_set_mode(jsdr_demod *d, int mode, int doagc)
+{
+    JSDR_REQUIRE(d && mode >= dsp::MODE_OFF && mode <= dsp::MODE_WFM, JSDR_EINVAL, "mode must be 0..4 (demod.java:39-43)");
+    d->mode = mode;
+    d->doagc = doagc != 0;
+    return JSDR_OK;
+}
+
+extern "C" int jsdr_demod_receive_audio_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
+                                            int16_t *audio, float *max_avg, int mem)
+{
+    JSDR_TRY(demod_check(d, iq, audio, S, chan_stride, mem));
+    if (S == 0) return JSDR_OK;
+    jsdr_ctx *ctx = d->ctx;
+    JSDR_TRY(ctx->bind());
+    const size_t n = (size_t)d->nchan * S;
+    float2 *res = nullptr;
+    JSDR_TRY(demod_run(d, iq, S, chan_stride, nullptr, mem, &res));
+    JSDR_TRY(grow(reinterpret_cast<void **>(&d->d_det), &d->det_cap, n * sizeof(float)));
+    int16_t *d_audio = audio;
+    float *d_ma = max_avg;
+    if (mem == JSDR_MEM_HOST) {
+        const size_t ma_off = (n * sizeof(int16_t) + 15) & ~(size_t)15;
+        JSDR_TRY(grow(reinterpret_cast<void **>(&d->d_audio), &d->audio_cap, ma_off + sizeof(float) * 2 * d->nchan));
+        d_audio = d->d_audio;
+        d_ma = reinterpret_cast<float *>(reinterpret_cast<char *>(d->d_audio) + ma_off);
+    }
+    // :409 fmgain = ad.rate / (MODE_NFM==mode ? 5000f : 75000f), int / float in float
+    const float fmgain = (float)d->rate / (d->mode == dsp::MODE_NFM ? 5000.0f : 75000.0f);
+    dsp::k_detect<<<d->nchan, 256, 0, ctx->stream>>>(res, S, d->mode, fmgain, d->doagc, d->d_lilq, d->d_det, d_audio, d_ma);
+    JSDR_TRY(launched(ctx, "k_detect"));
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMemcpyAsync(audio, d_audio, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (max_avg)
+            JSDR_CUDA(cudaMemcpyAsync(max_avg, d_ma, sizeof(float) * 2 * d->nchan, cudaMemcpyDeviceToHost, ctx->stream));
         JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return JSDR_OK;
@@ -539,4 +702,72 @@ extern "C" int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const i
         cudaFree(tmp);
     }
     return JSDR_OK;
+}
+
+// =========================================================================== waterfall.java
+// paintLine (waterfall.java:90-107): max-decimate one published "fft-psd" row to the pixel
+// width, map -100 dBFS..0 to 0..255, tint with the peak colour, rotate by half the width
+// (the row is in FFT order) and pack as ColorModel.getRGBdefault() ARGB.
+namespace jsdr {
+namespace dsp {
+__global__ void __launch_bounds__(256) k_waterfall(const float *__restrict__ psd, int n, int width, unsigned peak_rgb,
+                                                   int32_t *__restrict__ pix)
+{
+    const int row = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= width) return;
+    const float *a = psd + (size_t)row * (n + 2);
+    const float step = __fdiv_rn((float)n, (float)width);          // :61 (float)(length-2)/(float)getWidth()
+    const int o = java_f2i(__fmul_rn((float)p, step)), l = java_f2i(step);
+    float r = a[min(max(o, 0), n + 1)];                            // getMax (:109-116)
+    for (int i = o + 1; i < o + l && i < n + 2; i++)
+        if (a[i] > r) r = a[i];
+    int f = 255 - java_f2i(__fmul_rn(r, -2.55f));                  // :95
+    f = f < 0 ? 0 : f;
+    f = f > 255 ? 255 : f;
+    const int pr = (peak_rgb >> 16) & 255, pg = (peak_rgb >> 8) & 255, pb = peak_rgb & 255;
+    const unsigned c = 0xff000000u | ((unsigned)(pr * f / 256) << 16) | ((unsigned)(pg * f / 256) << 8) | (unsigned)(pb * f / 256);
+    pix[(size_t)row * width + (p + width / 2) % width] = (int32_t)c;   // :104 off = getWidth()/2
+}
+}  // namespace dsp
+}  // namespace jsdr
+
+extern "C" int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int rows, int width, uint32_t peak_rgb,
+                                   int32_t *pixels, int mem)
+{
+    JSDR_REQUIRE(ctx && psd && pixels, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(n > 0 && rows >= 0 && width > 0 && width <= n, JSDR_EINVAL, "need 0 < width <= n");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    if (rows == 0) return JSDR_OK;
+    JSDR_TRY(ctx->bind());
+    const float *d_psd = psd;
+    int32_t *d_pix = pixels;
+    void *tmp_in = nullptr, *tmp_out = nullptr;
+    const size_t in_bytes = sizeof(float) * (size_t)rows * (n + 2), out_bytes = sizeof(int32_t) * (size_t)rows * width;
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaMalloc(&tmp_in, in_bytes));
+        cudaError_t e = cudaMalloc(&tmp_out, out_bytes);
+        if (e != cudaSuccess) {
+            cudaFree(tmp_in);
+            set_error("jsdr_waterfall_rows: cudaMalloc: %s", cudaGetErrorString(e));
+            return JSDR_ENOMEM;
+        }
+        cudaMemcpyAsync(tmp_in, psd, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        d_psd = static_cast<const float *>(tmp_in);
+        d_pix = static_cast<int32_t *>(tmp_out);
+    }
+    dim3 grid((width + 255) / 256, rows);
+    dsp::k_waterfall<<<grid, 256, 0, ctx->stream>>>(d_psd, n, width, peak_rgb, d_pix);
+    int rc = launched(ctx, "k_waterfall");
+    if (mem == JSDR_MEM_HOST) {
+        if (rc == JSDR_OK) cudaMemcpyAsync(pixels, d_pix, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp_in);
+        cudaFree(tmp_out);
+        if (rc == JSDR_OK && e != cudaSuccess) {
+            set_error("jsdr_waterfall_rows: %s", cudaGetErrorString(e));
+            rc = JSDR_ECUDA;
+        }
+    }
+    return rc;
 }

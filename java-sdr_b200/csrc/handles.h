@@ -120,6 +120,12 @@ struct jsdr_demod {
     void *d_in = nullptr;
     float *d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
+    // detectors + AGC (demod.java:405-481)
+    int mode = 0, doagc = 0;         // MODE_OFF (:87 default)
+    float2 *d_lilq = nullptr;        // [nchan] li, lq of the FM discriminator (:67-68)
+    float *d_det = nullptr;          // [nchan][S] detector output scratch
+    int16_t *d_audio = nullptr;      // host-call staging: s16 audio + max/avg
+    size_t det_cap = 0, audio_cap = 0;
 };
 
 struct jsdr_fir {

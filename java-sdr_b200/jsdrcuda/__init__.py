@@ -101,6 +101,9 @@ _SIGS = {
     "jsdr_demod_get_weights": [_vp, _i, _vp],
     "jsdr_demod_set_flags": [_vp, _i, _i],
     "jsdr_demod_receive_f32": [_vp, _vp, _i, _i64, _vp, _i],
+    "jsdr_demod_set_mode": [_vp, _i, _i],
+    "jsdr_demod_receive_audio_f32": [_vp, _vp, _i, _i64, _vp, _vp, _i],
+    "jsdr_waterfall_rows": [_vp, _vp, _i, _i, _i, C.c_uint32, _vp, _i],
     "jsdr_fir_design": [_i, _i, _f, _vp],
     "jsdr_fir_nco_table": [_i, _f, _vp],
     "jsdr_fir_create": [_vp, _i, _i, _pp],
@@ -517,6 +520,32 @@ class demod:
         out = np.empty((self.nchan, 2 * S), dtype=np.float32)
         _ck(lib().jsdr_demod_receive_f32(self.h, _ptr(a), S, 0 if shared else S, _ptr(out), MEM_HOST))
         return out
+
+
+    MODE_OFF, MODE_RAW, MODE_AM, MODE_NFM, MODE_WFM = range(5)     # demod.java:39-43
+
+    def set_mode(self, mode: int, doagc: bool = False):
+        _ck(lib().jsdr_demod_set_mode(self.h, mode, int(doagc)))
+
+    def receive_audio(self, buf: np.ndarray, shared: bool | None = None):
+        """The whole of demod.receive (:398-481): returns (s16 audio [nchan, S], max_avg [nchan, 2])."""
+        a = np.ascontiguousarray(buf, dtype=np.float32)
+        if shared is None:
+            shared = a.ndim == 1
+        S = a.size // 2 if shared else a.size // (2 * self.nchan)
+        audio = np.empty((self.nchan, S), dtype=np.int16)
+        ma = np.empty((self.nchan, 2), dtype=np.float32)
+        _ck(lib().jsdr_demod_receive_audio_f32(self.h, _ptr(a), S, 0 if shared else S, _ptr(audio), _ptr(ma), MEM_HOST))
+        return audio, ma
+
+
+def waterfall_rows(ctx: "Context", psd: np.ndarray, width: int, peak_rgb: int = 0x00FFFF) -> np.ndarray:
+    """waterfall.paintLine (waterfall.java:90-107) for rows of published "fft-psd" arrays."""
+    a = np.ascontiguousarray(psd, dtype=np.float32)
+    a = a.reshape(-1, a.shape[-1])
+    pix = np.empty((a.shape[0], width), dtype=np.int32)
+    _ck(lib().jsdr_waterfall_rows(ctx.h, _ptr(a), a.shape[1] - 2, a.shape[0], width, peak_rgb, _ptr(pix), MEM_HOST))
+    return pix
 
 
 # ---------------------------------------------------------------------------- fir.java

@@ -159,6 +159,26 @@ class Demod:
         return out
 
 
+def demod_detect(sam: np.ndarray, mode: int, rate: int, doagc: bool, lilq: np.ndarray):
+    """demod.java:405-481 on the FIR/NCO output; lilq (float32[2]) is updated in place.
+    Returns (audio int16[n], max_avg float32[2])."""
+    sam = np.ascontiguousarray(sam, dtype=np.float32).ravel()
+    n = sam.size // 2
+    audio = np.empty(n, dtype=np.int16)
+    ma = np.empty(2, dtype=np.float32)
+    lib().orc_demod_detect(_p(sam, C.c_float), n, mode, rate, int(doagc), _p(lilq, C.c_float),
+                           _p(audio, C.c_int16), _p(ma, C.c_float))
+    return audio, ma
+
+
+def waterfall_row(psd: np.ndarray, width: int, peak_rgb: int = 0x00FFFF) -> np.ndarray:
+    """waterfall.java:90-107 for one published psd row (float[n+2])."""
+    psd = np.ascontiguousarray(psd, dtype=np.float32).ravel()
+    pix = np.empty(width, dtype=np.int32)
+    lib().orc_waterfall_row(_p(psd, C.c_float), psd.size - 2, width, C.c_uint32(peak_rgb), _p(pix, C.c_int32))
+    return pix
+
+
 # ---------------------------------------------------------------- FUNcubeBPSKDemod.java
 class _BpskS(C.Structure):
     _fields_ = [

@@ -421,6 +421,71 @@ void orc_demod_receive(orc_demod *s, const float *buf, int nsamples, float *out)
     }
 }
 
+static int j_f2i(float f)                    /* Java (int)float */
+{
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return INT_MAX;
+    if (f <= -2147483648.0f) return INT_MIN;
+    return (int)f;
+}
+
+void orc_demod_detect(const float *buf, int nsamples, int mode, int rate, int doagc,
+                      float lilq[2], int16_t *audio, float max_avg[2])
+{
+    float *sam = (float *)malloc(sizeof(float) * 2 * (size_t)(nsamples > 0 ? nsamples : 1));
+    float max = 0, avg = 0;                                             /* :405-406 */
+    float li = lilq[0], lq = lilq[1];
+    float fmgain = (float)rate / (mode == 3 ? 5000.0f : 75000.0f);      /* :409 */
+    for (int s = 0; s < 2 * nsamples; s += 2) {
+        sam[s] = buf[s];
+        sam[s + 1] = buf[s + 1];
+        if (mode == 0) {                                                /* :441-443 */
+            sam[s] = sam[s + 1] = 0;
+        } else if (mode == 1) {                                         /* :445-446 */
+        } else if (mode == 2) {                                         /* :448-451 */
+            float ss = sam[s] * sam[s] + sam[s + 1] * sam[s + 1];
+            sam[s] = (float)sqrt((double)ss);
+            avg = ((float)(s / 2) * avg + sam[s]) / (float)(s / 2 + 1);
+        } else {                                                        /* :453-461 */
+            float v = ((li * sam[s + 1]) - (lq * sam[s])) * fmgain;
+            li = sam[s];
+            lq = sam[s + 1];
+            sam[s] = v;
+        }
+        float a = fabsf(sam[s]);                                        /* :463 Math.max keeps NaN */
+        max = (max != max || a != a) ? NAN : (a > max ? a : max);
+    }
+    if (mode == 2) max -= avg;                                          /* :466-468 */
+    for (int s = 0; s < 2 * nsamples; s += 2) {                         /* :471-473 */
+        float x = (mode == 2 ? sam[s] - avg : sam[s]) * (doagc ? 1.0f / max : 1.0f);
+        audio[s / 2] = (int16_t)(j_f2i(x * 32767.0f) & 0xffff);
+    }
+    lilq[0] = li;
+    lilq[1] = lq;
+    max_avg[0] = max;
+    max_avg[1] = avg;
+    free(sam);
+}
+
+void orc_waterfall_row(const float *psd, int n, int width, uint32_t peak_rgb, int32_t *pix)
+{
+    float h = -2.55f;                                                   /* :92 */
+    float step = (float)n / (float)width;                               /* :61 */
+    int off = width / 2;                                                /* :62 */
+    int pr = (peak_rgb >> 16) & 255, pg = (peak_rgb >> 8) & 255, pb = peak_rgb & 255;
+    for (int p = 0; p < width; p++) {
+        int o = j_f2i((float)p * step), l = j_f2i(step);
+        float r = psd[o];                                               /* getMax :109-116 */
+        for (int i = o + 1; i < o + l; i++)
+            if (psd[i] > r) r = psd[i];
+        int f = 255 - j_f2i(r * h);
+        f = f < 0 ? 0 : f;
+        f = f > 255 ? 255 : f;
+        uint32_t c = 0xff000000u | ((uint32_t)(pr * f / 256) << 16) | ((uint32_t)(pg * f / 256) << 8) | (uint32_t)(pb * f / 256);
+        pix[(p + off) % width] = (int32_t)c;
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* FUNcubeBPSKDemod.java                                               */
 /* ------------------------------------------------------------------ */

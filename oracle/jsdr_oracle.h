@@ -83,6 +83,17 @@ void orc_demod_weights(orc_demod *s, int flo, int fhi); /* flo==INT32_MIN -> all
  * (what demod.java:436-437 copies to dbg[]) */
 void orc_demod_receive(orc_demod *s, const float *buf, int nsamples, float *out);
 
+/* The rest of demod.receive (demod.java:405-481) on the FIR/NCO output `sam` (2n floats):
+ * detector per mode (0 off, 1 raw, 2 AM, 3 NFM, 4 WFM; :439-463), max/avg, AGC, s16
+ * narrowing (:469-473).  lilq carries li/lq across blocks.  audio: n shorts (one channel of
+ * the stereo pair the reference writes); max_avg[0]=max (after the AM fix-up), [1]=avg. */
+void orc_demod_detect(const float *sam, int nsamples, int mode, int rate, int doagc,
+                      float lilq[2], int16_t *audio, float max_avg[2]);
+
+/* waterfall.paintLine (waterfall.java:90-107): one published psd row (float[n+2]) to `width`
+ * ARGB pixels, peak colour 0xRRGGBB. */
+void orc_waterfall_row(const float *psd, int n, int width, uint32_t peak_rgb, int32_t *pix);
+
 /* ---- FUNcubeBPSKDemod.java:366-595 ------------------------------------- */
 #define ORC_MAX_DS_TAPS 128
 typedef struct {

@@ -247,3 +247,38 @@ def test_s16_division_shortcut_is_exact_for_every_input():
         e = rnd32(xf - Fraction(float(q0)) * 32767)
         q = rnd32(Fraction(float(q0)) + fr_r * Fraction(float(e)))
         assert q == f32(x) / f32(32767.0), x
+
+
+def test_demod_detectors_known_answers():
+    """demod.java:439-473 — AM of a constant envelope is silence after the mean is removed,
+    FM of a pure tone is a constant proportional to its frequency, RAW passes I through."""
+    n, rate = 4000, 96000
+    t = np.arange(n)
+    tone = 0.5 * np.exp(2j * np.pi * 3000.0 * t / rate)
+    sam = np.empty(2 * n, np.float32)
+    sam[0::2], sam[1::2] = tone.real, tone.imag
+    lilq = np.zeros(2, np.float32)
+    audio, ma = O.demod_detect(sam, 2, rate, False, lilq)                    # AM
+    assert abs(ma[1] - 0.5) < 1e-6 and np.max(np.abs(audio)) <= 1           # envelope 0.5, mean removed
+    lilq = np.zeros(2, np.float32)
+    audio, ma = O.demod_detect(sam, 3, rate, False, lilq)                    # NFM, gain rate/5000
+    want = 0.25 * np.sin(2 * np.pi * 3000.0 / rate) * (rate / 5000.0)
+    assert np.allclose(audio[1:] / 32767.0, want, atol=2e-4) and audio[0] == 0     # li=lq=0 before the first sample
+    assert np.allclose(lilq, [sam[-2], sam[-1]])
+    audio, _ = O.demod_detect(sam, 1, rate, True, np.zeros(2, np.float32))   # RAW with AGC: peak -> full scale
+    assert np.max(np.abs(audio)) >= 32766
+    audio, _ = O.demod_detect(sam, 0, rate, True, np.zeros(2, np.float32))   # OFF with AGC: 0 * inf = NaN -> 0
+    assert np.all(audio == 0)
+
+
+def test_waterfall_row_known_answers():
+    """waterfall.java:90-107 — 0 dBFS maps to the full peak colour, -100 dBFS to black, the row is
+    rotated by half the width and each pixel takes the maximum of its bins."""
+    n, width = 4096, 512
+    psd = np.full(n + 2, -100.0, np.float32)
+    psd[0] = 0.0                       # DC bin -> pixel 0 before the rotation
+    psd[8 * 100 + 3] = -50.0           # inside pixel 100's 8 bins
+    pix = O.waterfall_row(psd, width).view(np.uint32)
+    assert pix[(0 + width // 2) % width] == 0xFF00FEFE                       # cyan * 255/256
+    assert pix[(100 + width // 2) % width] == 0xFF000000 | (255 * 128 // 256) << 8 | (255 * 128 // 256)
+    assert pix[(200 + width // 2) % width] == 0xFF000000
