@@ -56,14 +56,16 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     jsdr_ctx *ctx = new jsdr_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    {   // the side stream carries the serial, data-independent phase replay: highest priority, so
-        // that its few small CTAs are placed as soon as a slot frees up instead of queueing behind
-        // the whole grid of the data kernel that runs beside it
+    {   // three priorities: the side stream carries the serial, data-independent phase replay and
+        // goes first, so that its few CTAs are placed as soon as a slot frees up instead of queueing
+        // behind the whole grid of a data kernel; the main stream is in the middle; the auxiliary
+        // stream (the pump's FFT when it runs beside the decimator) fills what is left
         int lo = 0, hi = 0;
         JSDR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        if (getenv("JSDR_SIDE_PRIORITY") && atoi(getenv("JSDR_SIDE_PRIORITY")) == 0) hi = lo;   // (tuning aid)
+        const int mid = (hi < lo) ? lo - 1 : lo;
+        JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mid));
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi));
+        JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, lo));
     }
     JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
@@ -73,6 +75,8 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     }
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t0));
     JSDR_CUDA(cudaEventCreate(&ctx->ev_t1));
+    JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux_fork, cudaEventDisableTiming));
+    JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux_join, cudaEventDisableTiming));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     *out = ctx;
@@ -87,6 +91,8 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
     cudaStreamSynchronize(ctx->side);
     cudaEventDestroy(ctx->ev_t0);
     cudaEventDestroy(ctx->ev_t1);
+    cudaEventDestroy(ctx->ev_aux_fork);
+    cudaEventDestroy(ctx->ev_aux_join);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
     for (auto *v : {&ctx->spans, &ctx->free_spans})
@@ -98,6 +104,7 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
         cudaEventDestroy(ctx->ev_chunk_in[i]);
         cudaEventDestroy(ctx->ev_chunk_done[i]);
     }
+    cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
     cudaStreamDestroy(ctx->stream);
@@ -113,6 +120,7 @@ extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
     JSDR_CUDA(cudaStreamSynchronize(ctx->side));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
 }
 

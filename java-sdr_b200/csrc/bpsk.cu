@@ -845,11 +845,10 @@ int bpsk_reset_ds(jsdr_bpsk *b)
 }
 
 // The streaming tuner + decimator: one lane per channel, one warp per segment of R outputs.
-template <int PREC, int NTAPS, int DD>
-int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
+template <int PREC, int NTAPS, int DD, int W>
+int launch_stream_w(jsdr_bpsk *b, const stream::Params &sp)
 {
     jsdr_ctx *ctx = b->ctx;
-    constexpr int W = stream::kWarps;
     auto kern = stream::k_mixdecim_stream<PREC, NTAPS, DD, W>;
     constexpr size_t smem = stream::smem_bytes<W, DD>();
     static bool attr_done = false;
@@ -862,6 +861,25 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
     ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
     kern<<<grid, W * 32, smem, ctx->stream>>>(sp);
     return launched(ctx, "k_mixdecim_stream");
+}
+
+static int pump_concurrent()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("JSDR_PUMP_CONCURRENT");      // (tuning aid)
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+// Whole-SM CTAs (15 warps) normally; 8-warp CTAs when the pump runs the FFT beside the decimator,
+// so that FFT CTAs fit on the same SM.
+template <int PREC, int NTAPS, int DD>
+int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
+{
+    if (sp.warps_per_cta == stream::kWarpsShared) return launch_stream_w<PREC, NTAPS, DD, stream::kWarpsShared>(b, sp);
+    return launch_stream_w<PREC, NTAPS, DD, stream::kWarps>(b, sp);
 }
 
 int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
@@ -887,7 +905,8 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     // about three per resident warp, their count chosen so that the last wave is full.
     const int scout_ctas = (mp.nchan + scout_threads() - 1) / scout_threads();
     sp.grid = std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
-    const int resident = sp.grid * stream::kWarps;
+    sp.warps_per_cta = (b->share_sm && pump_concurrent()) ? stream::kWarpsShared : stream::kWarps;
+    const int resident = sp.grid * sp.warps_per_cta;
     int nseg = std::max(1, 3 * resident / sp.ncw);
     int R = (mp.NO + nseg - 1) / nseg;
     if (R < 64) R = 64;
@@ -1427,8 +1446,15 @@ struct PumpJob {
 int pump_fft(void *user, const void *d_in)
 {
     PumpJob *j = static_cast<PumpJob *>(user);
-    return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc,
-                       j->f->ctx->stream);
+    jsdr_ctx *ctx = j->f->ctx;
+    if (!pump_concurrent())
+        return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream);
+    // beside the decimator: fork to the low-priority auxiliary stream; the caller joins
+    JSDR_CUDA(cudaEventRecord(ctx->ev_aux_fork, ctx->stream));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_aux_fork, 0));
+    JSDR_TRY(fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->aux));
+    JSDR_CUDA(cudaEventRecord(ctx->ev_aux_join, ctx->aux));
+    return JSDR_OK;
 }
 }  // namespace
 
@@ -1455,7 +1481,11 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     if (mem == JSDR_MEM_DEVICE) {
         job.d_psd = psd;
         job.d_peak = peak_bin;
-        return bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
+        b->share_sm = 1;
+        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
+        b->share_sm = 0;
+        if (rc == JSDR_OK && pump_concurrent()) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux_join, 0));
+        return rc;
     }
     if (f->out_cap < psd_elems * sizeof(float)) {
         cudaFree(f->d_out);

@@ -33,6 +33,7 @@ namespace bpsk {
 namespace stream {
 
 constexpr int kWarps = 15;
+constexpr int kWarpsShared = 8;       // CTA size when another kernel's CTAs share the SM
 constexpr int kMaxTaps = 64;
 enum { PREC_F64 = 0, PREC_F32 = 1 };
 
@@ -48,6 +49,7 @@ struct Params {
     const double2 *cossin;              // [257] (cos, sin); entry 256 = (1, 1), the mixer bypass
     int n0, NO, R, nseg, ncw;           // first output's sample, outputs, outputs per segment, segments, channel groups
     int grid;                           // CTAs to launch (host side only)
+    int warps_per_cta;                  // kWarps or kWarpsShared (host side only)
     double2 *ds_out;
     int max_ds;
     double taps[kMaxTaps];
@@ -211,7 +213,7 @@ __device__ __forceinline__ void period_body(const Params &p, const uint32_t *myr
 }
 
 template <int PREC, int NTAPS, int DD, int W>
-__global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
+__global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(const Params p)
 {
     constexpr int NQ = (NTAPS + DD - 1) / DD;          // live outputs per sample
     constexpr int kPitch = row_pitch<DD>();

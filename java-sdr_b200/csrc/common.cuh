@@ -50,6 +50,8 @@ struct jsdr_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;   // main stream: data kernels
     cudaStream_t side = nullptr;     // side stream: data-independent phase scouts
+    cudaStream_t aux = nullptr;      // low priority: work that runs beside the main stream's kernel
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies of the chunked host path
     cudaEvent_t ev_chunk_in[16] = {nullptr}, ev_chunk_done[16] = {nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
