@@ -1,8 +1,12 @@
 // fft.cu — host side of the fft.java replacement (jsdr_fft_* in jsdrcuda.h).
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include <vector>
 
+#include "fft_fourstep.cuh"
 #include "fft_generic.cuh"
 #include "fft_kernels.cuh"
 #include "fft_plans.h"
@@ -95,6 +99,89 @@ __global__ void __launch_bounds__(256) k_generic_psd(const float2 *__restrict__ 
     }
 }
 
+
+// ---- 32768 / 65536: the four-step pair (fft_fourstep.cuh), chunked so that Z stays in L2 ----
+template <int N1, int IN, int OUT>
+static int launch_fourstep_chunk(jsdr_ctx *ctx, const FsArgs &fa, cudaStream_t st)
+{
+    constexpr int N2 = 256;
+    {
+        ProfScope prof(ctx, JSDR_K_FFT, st);
+        k_fs_cols<N1, N2, IN><<<(unsigned)((long)fa.nblocks * (N2 / 16)), 256, 0, st>>>(fa);
+        JSDR_TRY(launched(ctx, "k_fs_cols"));
+    }
+    ProfScope prof(ctx, JSDR_K_FFT, st);
+    k_fs_rows<N1, N2, OUT><<<(unsigned)((long)fa.nblocks * (N1 / 16)), 256, 0, st>>>(fa);
+    return launched(ctx, "k_fs_rows");
+}
+
+static int launch_fourstep(jsdr_fft *f, const Args &a, int in_fmt, int out_mode, cudaStream_t st)
+{
+    jsdr_ctx *ctx = f->ctx;
+    const int N = f->n, N1 = f->fs_n1;
+    static int chunk_mb = 0;
+    if (!chunk_mb) {
+        const char *e = getenv("JSDR_FS_CHUNK_MB");             // (tuning aid) size of Z per chunk
+        chunk_mb = e ? std::max(1, atoi(e)) : 48;
+    }
+    const int chunk = std::max(1, std::min(f->max_batch, (int)(((long)chunk_mb << 20) / ((long)N * 8))));
+    if (!f->d_work[0]) {
+        cudaError_t e = cudaMalloc(&f->d_work[0], (size_t)chunk * N * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_work[1], (size_t)chunk * N * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_best, sizeof(unsigned long long) * (size_t)f->max_batch);
+        if (e != cudaSuccess) {
+            set_error("fft workspace: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return JSDR_ENOMEM;
+        }
+    }
+    if (out_mode == OUT_PSD)
+        JSDR_CUDA(cudaMemsetAsync(f->d_best, 0, sizeof(unsigned long long) * (size_t)a.nblocks, st));
+    // Chunks alternate between two streams (and two Z buffers): while one chunk's row kernel
+    // drains, the next chunk's column kernel already fills the SMs.
+    const bool two = a.nblocks > chunk && st != ctx->aux;
+    if (two) {
+        JSDR_CUDA(cudaEventRecord(ctx->ev_aux_fork, st));
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_aux_fork, 0));
+    }
+    const size_t in_el = (in_fmt == IN_S16) ? 4 : 8;
+    int ci = 0;
+    for (int b0 = 0; b0 < a.nblocks; b0 += chunk, ci++) {
+        cudaStream_t cs = (two && (ci & 1)) ? ctx->aux : st;
+        FsArgs fa;
+        fa.nblocks = std::min(chunk, a.nblocks - b0);
+        fa.in = reinterpret_cast<const char *>(a.in) + (size_t)b0 * N * in_el;
+        fa.z = f->d_work[ci & 1];
+        fa.out = (out_mode == OUT_PSD) ? a.out + (size_t)b0 * (N + 2) : a.out + (size_t)b0 * N * 2;
+        fa.best = f->d_best + b0;
+        fa.tw = a.tw;
+        fa.cf = a.cf;
+        fa.ic = a.ic;
+        fa.qc = a.qc;
+        int rc;
+        if (out_mode == OUT_SPECTRUM) {
+            rc = (N1 == 128) ? launch_fourstep_chunk<128, IN_F32, OUT_SPECTRUM>(ctx, fa, cs)
+                             : launch_fourstep_chunk<256, IN_F32, OUT_SPECTRUM>(ctx, fa, cs);
+        } else if (in_fmt == IN_F32) {
+            rc = (N1 == 128) ? launch_fourstep_chunk<128, IN_F32, OUT_PSD>(ctx, fa, cs)
+                             : launch_fourstep_chunk<256, IN_F32, OUT_PSD>(ctx, fa, cs);
+        } else {
+            rc = (N1 == 128) ? launch_fourstep_chunk<128, IN_S16, OUT_PSD>(ctx, fa, cs)
+                             : launch_fourstep_chunk<256, IN_S16, OUT_PSD>(ctx, fa, cs);
+        }
+        JSDR_TRY(rc);
+    }
+    if (two) {
+        JSDR_CUDA(cudaEventRecord(ctx->ev_aux_join, ctx->aux));
+        JSDR_CUDA(cudaStreamWaitEvent(st, ctx->ev_aux_join, 0));
+    }
+    if (out_mode == OUT_PSD) {
+        k_fs_finish<<<(a.nblocks + 127) / 128, 128, 0, st>>>(f->d_best, a.out, a.peak_bin, N, a.rate, a.nblocks);
+        JSDR_TRY(launched(ctx, "k_fs_finish"));
+    }
+    return JSDR_OK;
+}
+
 static int launch_generic(jsdr_fft *f, const Args &a, int in_fmt, int out_mode, cudaStream_t st)
 {
     jsdr_ctx *ctx = f->ctx;
@@ -144,6 +231,11 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
     a.cf = cf;
     a.ic = ic;
     a.qc = qc;
+    if (out_mode == OUT_SPECTRUM && in_fmt != IN_F32) {
+        set_error("spectrum output needs float input");
+        return JSDR_EINVAL;
+    }
+    if (f->fs_n1) return launch_fourstep(f, a, in_fmt, out_mode, st);
     if (!f->launch) return launch_generic(f, a, in_fmt, out_mode, st);
     return reinterpret_cast<launch_fn>(f->launch)(f->ctx, a, in_fmt, out_mode, st);
 }
@@ -156,6 +248,7 @@ using namespace jsdr;
 extern "C" int jsdr_fft_supported(int n)
 {
     if (fft::find_plan(n)) return 1;                       // single-CTA plan
+    if (n == 32768 || n == 65536) return 3;                // four-step pair
     return n >= 2 && fftg::make_plan(n).nstages > 0 ? 2 : 0;   // staged path (slower)
 }
 
@@ -174,7 +267,8 @@ extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, js
     f->n = n;
     f->rate = rate;
     f->max_batch = max_batch;
-    f->launch = p ? reinterpret_cast<void *>(p->fn) : nullptr;   // null: the staged path
+    f->launch = p ? reinterpret_cast<void *>(p->fn) : nullptr;   // null: four-step or the staged path
+    f->fs_n1 = (!p && n == 32768) ? 128 : (!p && n == 65536) ? 256 : 0;
     // twiddle table exp(-2*pi*i*t/n), computed in double, rounded once
     std::vector<float2> tw(n);
     for (int t = 0; t < n; t++) {
@@ -209,6 +303,7 @@ extern "C" int jsdr_fft_destroy(jsdr_fft *f)
     cudaFree(f->d_peak);
     cudaFree(f->d_work[0]);
     cudaFree(f->d_work[1]);
+    cudaFree(f->d_best);
     delete f;
     return JSDR_OK;
 }

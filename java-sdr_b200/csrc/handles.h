@@ -13,7 +13,9 @@ struct jsdr_fft {
     int n = 0, rate = 0, max_batch = 0;
     void *launch = nullptr;          // jsdr::fft::launch_fn of the plan
     float2 *d_tw = nullptr;          // exp(-2*pi*i*t/n)
-    float2 *d_work[2] = {nullptr, nullptr};   // ping-pong workspace of the staged path (no single-CTA plan)
+    float2 *d_work[2] = {nullptr, nullptr};   // workspace of the four-step / staged paths (no single-CTA plan)
+    unsigned long long *d_best = nullptr;     // [max_batch] packed block maxima (four-step path)
+    int fs_n1 = 0;                            // four-step factor N1 (128 or 256), 0 otherwise
     // staging for host-pointer calls (allocated on first use)
     void *d_in = nullptr;
     float *d_out = nullptr;
