@@ -41,7 +41,7 @@ D = RATE // 9600
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=4096, help="independent streams per GPU")
@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)],
+                                          "-lms", "20", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -276,6 +276,18 @@ def main():
     other_ms = ctx.timer_stop_ms() / max(2, a.steps // 2)
     bank.set_precision(J.PREC_F32 if a.precision == "f32" else J.PREC_F64)
 
+    # ---- the whole FUNcube chain to bits (27-tap decimator, matched filter, bit timing) on the
+    # same resident batch, for the record: the reference's own receiver shape at 192 kS/s
+    bank_c = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S, stages=3)
+    for _ in range(2):
+        bank_c.receive_dev(d_raw, S, S, s16=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(3):
+        bank_c.receive_dev(d_raw, S, S, s16=True)
+    chain_ms = ctx.timer_stop_ms() / 3
+    bank_c.close()
+
     # ---- end to end through the C ABI with host (pinned) buffers
     e_ch = min(a.e2e_channels, nchan)
     e_batch = e_ch * nblk
@@ -308,8 +320,8 @@ def main():
     if dist is not None:
         import torch
         dev = torch.device("cuda", local)
-    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms), launches = sharding.reduce_timing(
-        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms], launches)
+    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms), launches = sharding.reduce_timing(
+        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms], launches)
     launches = int(launches)
 
     if rank == 0:
@@ -357,7 +369,11 @@ def main():
                                       "note": "4 B in (read once) + 4 B PSD + 16/D B decimated out per sample"}},
             "variants": {"decimator_" + other: {"value": round(world * samples / (other_ms * 1e-3) / 1e6, 1),
                                                 "unit": "Msamples/s", "ms_per_step": round(other_ms, 4),
-                                                "note": "same pipeline with the tuner+decimator in %s" % other}},
+                                                "note": "same pipeline with the tuner+decimator in %s" % other},
+                         "funcube_chain_to_bits": {"value": round(world * samples / (chain_ms * 1e-3) / 1e6, 1),
+                                                   "unit": "Msamples/s", "ms_per_step": round(chain_ms, 4),
+                                                   "note": "tuner + 27-tap decimator + 65-tap matched filter + bit timing "
+                                                           "(FUNcubeBPSKDemod.java:382-595), bit-exact, same resident batch"}},
             "e2e": {"value": round(world * e2e_samples / e2e_s / 1e6, 1), "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "sample": f"{e_ch} channels x {nblk} blocks per rank through jsdr_pump_receive_s16 + jsdr_bpsk_read_ds with pinned host buffers"},

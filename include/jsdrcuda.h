@@ -172,6 +172,22 @@ int jsdr_bpsk_read_counters(jsdr_bpsk *b, int64_t *counters);
 /* device pointer of the decimated output for zero-copy consumers */
 int jsdr_bpsk_ds_device_ptr(jsdr_bpsk *b, double **dev_ptr);
 
+/* The frame stage behind the bits (FUNcubeBPSKDemod.java:553-574, FECDecoder.java:703-852):
+ * once enabled, every receive call (stages == 3) also runs the sync correlator over the
+ * new bits (65-point correlation with SYNC_VECTOR at stride 80 across the last 5200 bits,
+ * >= 45 starts a decode) and FECDecode on every hit: de-interleave, Viterbi K=7 r=1/2,
+ * de-scramble, two RS(160,128) decoders, re-encode and count channel errors.
+ * mettab is the Viterbi metric table int16[2][256] (a literal in FECDecoder.java:67-100;
+ * the caller passes the reference's own array).  read_frames returns this call's frames
+ * ordered by (channel, bit): errors is FECDecode's return value (channel errors, or -1 if
+ * an RS block failed, data then zero); bit_index is cntBit of the bit that completed the
+ * frame; *nframes is the number detected (it can exceed max_frames, the rest are dropped).
+ * read_fec_counters: cntFEC and cntDec per channel (:567,571). */
+int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max_frames_per_call);
+int jsdr_bpsk_read_frames(jsdr_bpsk *b, int32_t *nframes, int32_t *chan, int64_t *bit_index,
+                          int32_t *errors, uint8_t *data /* max_frames*256 */, int max_frames);
+int jsdr_bpsk_read_fec_counters(jsdr_bpsk *b, int64_t *cnt_fec, int64_t *cnt_dec);
+
 /* ------------------------------------------------------------------ demod.java
  * FIR band-pass + NCO down-shift part of demod.receive (demod.java:410-434) for
  * nchan channels: 21-tap complex FIR with float taps and float accumulation in

@@ -1156,6 +1156,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     }
     if (NO == 0)   // nothing reached the 9600 S/s stage in this call: no bits either
         JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * nchan, ctx->stream));
+    if (b->fec && b->stages >= 3 && b->d_bits) JSDR_TRY(jsdr_fec_after_bits(b));   // :553-574
     b->cnt_ds += NO;
     if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
@@ -1267,6 +1268,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
                     b->d_bit_roll, b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_out, b->d_ts, b->d_bits,
                     b->d_bit_at, b->d_nbits, b->d_in, b->d_at_work[0], b->d_at_work[1], b->d_at_rev[0], b->d_at_rev[1], b->d_at_state};
     for (void *p : ptrs) cudaFree(p);
+    jsdr_fec_destroy(b);
     for (int i = 0; i < 2; i++) {
         if (b->plan[i].ready) cudaEventDestroy(b->plan[i].ready);
         if (b->plan[i].consumed) cudaEventDestroy(b->plan[i].consumed);

@@ -47,8 +47,11 @@ constexpr int kDmTaps = 65;          // MATCHED_FILTER_SIZE
 }  // namespace bpsk
 }  // namespace jsdr
 
+struct jsdr_fec_state;   // fec.cu
+
 struct jsdr_bpsk {
     jsdr_ctx *ctx = nullptr;
+    jsdr_fec_state *fec = nullptr;   // sync correlator + FEC stage, when enabled
     int rate = 0, D = 0, nchan = 0, max_block = 0, stages = 3;
     int ntaps = 27;
     int max_ds = 0, max_words = 0, max_bits = 0;
@@ -140,6 +143,9 @@ struct jsdr_fir {
     int32_t *d_in = nullptr, *d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
 };
+
+int jsdr_fec_after_bits(jsdr_bpsk *b);   // fec.cu: run the frame stage on the bits of the last receive
+void jsdr_fec_destroy(jsdr_bpsk *b);
 
 namespace jsdr {
 namespace fft {

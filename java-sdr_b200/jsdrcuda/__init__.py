@@ -84,6 +84,9 @@ _SIGS = {
     "jsdr_bpsk_set_tuning": [_vp, _i, _d],
     "jsdr_bpsk_set_autotune": [_vp, _i, _i],
     "jsdr_bpsk_read_centre": [_vp, _vp],
+    "jsdr_bpsk_enable_fec": [_vp, _vp, _i],
+    "jsdr_bpsk_read_frames": [_vp, _vp, _vp, _vp, _vp, _vp, _i],
+    "jsdr_bpsk_read_fec_counters": [_vp, _vp, _vp],
     "jsdr_bpsk_set_precision": [_vp, _i],
     "jsdr_bpsk_set_kernel": [_vp, _i],
     "jsdr_bpsk_set_ds_filter": [_vp, _vp, _i],
@@ -403,6 +406,31 @@ class FUNcubeBPSKDemod:
         out = np.zeros(self.nchan, dtype=np.int32)
         _ck(lib().jsdr_bpsk_read_centre(self.h, _ptr(out)))
         return out
+
+    def enable_fec(self, mettab: np.ndarray, max_frames: int = 64):
+        """Sync correlator + FECDecode behind the bits (:553-574, FECDecoder.java:703-852).
+        mettab: FECDecoder's metric table, int16[2, 256]."""
+        t = np.ascontiguousarray(mettab, dtype=np.int16).reshape(2, 256)
+        self._max_frames = max_frames
+        _ck(lib().jsdr_bpsk_enable_fec(self.h, _ptr(t), max_frames))
+
+    def read_frames(self):
+        """[(channel, bit_index, errors, data uint8[256])] of the last receive, by (channel, bit)."""
+        mf = self._max_frames
+        n = np.zeros(1, dtype=np.int32)
+        chan = np.zeros(mf, dtype=np.int32)
+        at = np.zeros(mf, dtype=np.int64)
+        err = np.zeros(mf, dtype=np.int32)
+        data = np.zeros((mf, 256), dtype=np.uint8)
+        _ck(lib().jsdr_bpsk_read_frames(self.h, _ptr(n), _ptr(chan), _ptr(at), _ptr(err), _ptr(data), mf))
+        k = min(int(n[0]), mf)
+        return [(int(chan[i]), int(at[i]), int(err[i]), data[i].copy()) for i in range(k)]
+
+    def fec_counters(self):
+        a = np.zeros(self.nchan, dtype=np.int64)
+        d = np.zeros(self.nchan, dtype=np.int64)
+        _ck(lib().jsdr_bpsk_read_fec_counters(self.h, _ptr(a), _ptr(d)))
+        return a, d
 
     def set_precision(self, precision: int):
         _ck(lib().jsdr_bpsk_set_precision(self.h, precision))
