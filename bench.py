@@ -112,7 +112,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside the timed region (host clock, 30 ms slack)."""
+        self.t0, self.t1 = t0 - 0.03, t1 + 0.03
 
     def stop(self):
         if not self.proc:
@@ -124,7 +128,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1):
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -242,19 +249,21 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs a moment to start: begin before the warm-up
     for _ in range(a.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = ctx.launch_count()
     ctx.profile(True)            # CUDA events around every kernel launch, on the stream it is launched on
     ctx.profile_read()
+    t_wall0 = time.time()
     ctx.timer_start()
     for _ in range(a.steps):
         step()
     ms = ctx.timer_stop_ms()
+    sampler.window(t_wall0, time.time())
     launches = ctx.launch_count() - l0
     kern = ctx.profile_read()    # {kind: (total ms, launches)} inside the timed region
     ctx.profile(False)
