@@ -129,3 +129,31 @@ def test_pump_host_path_chunked_equals_separate_handlers(ctx):
         assert np.array_equal(b1.read_ds(), b2.read_ds())
     for h in (f, b1, b2):
         h.close()
+
+
+def test_full_size_bank_stream_equals_tile_and_is_linear(ctx):
+    """BASELINE config 4's full bank (4096 channels, 192 kS/s, 64 taps, D=20) on 32768-sample
+    blocks: the streaming kernel (every SM, several segments per channel, phase checkpoints
+    from the look-ahead scout) must equal the tile kernel bit for bit on every channel, and a
+    sample of channels must equal the oracle."""
+    rate, nchan, S = 192000, 4096, 32768
+    rng = np.random.default_rng(77)
+    from jsdrcuda import sharding
+    tun = sharding.channel_tuning(0, nchan)
+    taps = siggen.lowpass_taps(64, 4800.0, rate)
+    a = make_bank(ctx, rate, tun, taps, J.KERNEL_STREAM, max_block=S)
+    b = make_bank(ctx, rate, tun, taps, J.KERNEL_TILE, max_block=S)
+    base = rng.integers(-32768, 32768, (64, 2 * S)).astype(np.int16)
+    raw = np.ascontiguousarray(np.tile(base, (nchan // 64, 1)))
+    orcs = {c: O.Bpsk(rate, tun[c], ds_taps=taps, stages=1) for c in (0, 1777, 4095)}
+    for k in range(2):
+        raw = np.roll(raw, 12345 * (k + 1), axis=1)
+        a.receive_raw(raw)
+        b.receive_raw(raw)
+        da, db = a.read_ds(), b.read_ds()
+        assert da.shape == db.shape and da.shape[0] == nchan and abs(da.shape[1] - S / 20) < 1
+        assert np.array_equal(da, db), k
+        for c, o in orcs.items():
+            assert np.array_equal(da[c], o.receive(O.s16_to_float(raw[c]))["ds"]), (k, c)
+    a.close()
+    b.close()
