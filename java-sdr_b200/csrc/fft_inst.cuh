@@ -1,6 +1,8 @@
 // fft_inst.cuh — one translation unit per FFT length includes this with
 // JSDR_FFT_N etc. defined, so the plans compile in parallel.
 #pragma once
+#include <algorithm>
+
 #include "fft_kernels.cuh"
 
 namespace jsdr {
@@ -17,6 +19,15 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
     }
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
+    if constexpr (P::PERSIST) {   // resident CTAs loop over the blocks
+        static int resident = 0;
+        if (!resident) {
+            int per_sm = 0;
+            JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, P::SMEM));
+            resident = std::max(1, per_sm) * ctx->sm_count;
+        }
+        grid = std::min(grid, resident);
+    }
     ProfScope prof(ctx, JSDR_K_FFT, st);
     kern<<<grid, P::T, P::SMEM, st>>>(a);
     return launched(ctx, "fft_kernel");

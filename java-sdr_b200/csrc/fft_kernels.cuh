@@ -291,6 +291,13 @@ struct Plan {
     static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
     static_assert(R0_ % 2 == 0 && ML % 2 == 0, "chunk scatter uses 16-byte stores");
     static_assert(G_ == 1 || T_ == G_ * ML, "multi-block CTAs need one last-pass round");
+    // Blocks that fill most of an SM's shared memory leave one to three CTAs per SM, too few to
+    // hide the load phase behind other CTAs' butterflies.  Those plans run persistent CTAs that
+    // fetch the next block's pass-0 samples into registers before the last pass of the current
+    // one (s16 input: one register per sample).
+    static constexpr bool PERSIST = (G_ == 1) && (N_ >= 9600);
+    static constexpr int NB0 = N_ / R0_;
+    static constexpr int PRE_IT = (NB0 + T_ - 1) / T_;        // pass-0 butterflies per thread
 };
 
 struct Args {
@@ -340,6 +347,17 @@ __device__ __forceinline__ float2 load_sample(const Args &a, long blk, int n)
     }
 }
 
+__device__ __forceinline__ float2 s16_pair_to_float(const Args &a, uint32_t w)
+{   // as in load_sample
+    if (a.ic | a.qc) {
+        w = (((w & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((w >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
+    }
+    w ^= 0x80008000u;
+    float fi = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)) - 8421376.0f;
+    float fq = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)) - 8421376.0f;
+    return make_float2(fi, fq);
+}
+
 template <int R, int M>
 __device__ __forceinline__ void load_strided(float2 *v, const float2 *p)
 {
@@ -377,8 +395,32 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
     __shared__ int s_idx[P::G];
 
     const int tid = threadIdx.x;
-    const long blk0 = (long)blockIdx.x * P::G;
     constexpr int N = P::N;
+    constexpr bool PREFETCH = P::PERSIST && IN == IN_S16;
+
+    // pass-0 samples of the next block (persistent plans, s16 input)
+    uint32_t pre[PREFETCH ? P::PRE_IT : 1][PREFETCH ? P::R0 : 1];
+    auto prefetch = [&](long blk) {
+        if constexpr (PREFETCH) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in) + blk * N;
+#pragma unroll
+            for (int it = 0; it < P::PRE_IT; it++) {
+                const int c = tid + it * P::T;
+                if (c < P::NB0) {
+#pragma unroll
+                    for (int m = 0; m < P::R0; m++) pre[it][m] = ldg_stream_u32(src + c + m * P::NB0);
+                }
+            }
+        }
+    };
+    if constexpr (PREFETCH) {
+        if ((long)blockIdx.x < a.nblocks) prefetch(blockIdx.x);
+    }
+
+    // one pass for ordinary plans (a CTA owns blocks blk0 .. blk0+G-1); persistent plans loop
+    long blk0 = (long)blockIdx.x * P::G;
+    const long blk_step = gridDim.x;
+    do {
 
     if (OUT == OUT_PSD && tid < P::G) {
         s_max[tid] = 0u;
@@ -389,13 +431,20 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
     {
         constexpr int R0 = P::R0;
         constexpr int NB0 = N / R0;
-        for (int U = tid; U < P::G * NB0; U += P::T) {
+#pragma unroll
+        for (int it = 0; it < (PREFETCH ? P::PRE_IT : 1); it++) {
+        for (int U = PREFETCH ? tid + it * P::T : tid; U < P::G * NB0; U += PREFETCH ? P::G * NB0 : P::T) {
             int g = U / NB0, c = U - g * NB0;
             long blk = blk0 + g;
             if (blk >= a.nblocks) continue;
             float2 v[R0];
+            if constexpr (PREFETCH) {
 #pragma unroll
-            for (int m = 0; m < R0; m++) v[m] = load_sample<P, IN>(a, blk, c + m * NB0);
+                for (int m = 0; m < R0; m++) v[m] = s16_pair_to_float(a, pre[it][m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < R0; m++) v[m] = load_sample<P, IN>(a, blk, c + m * NB0);
+            }
             Dft<R0>::run(v);
             int pos;
             if constexpr (P::K == 2) {
@@ -413,6 +462,7 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
             for (int m = 0; m < R0 / 2; m++)
                 dst[m] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
         }
+        }
     }
     __syncthreads();
 
@@ -427,6 +477,9 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
     }
 
     // ---------------- last pass + epilogue
+    if constexpr (PREFETCH) {
+        if (blk0 + blk_step < a.nblocks) prefetch(blk0 + blk_step);   // in flight behind the last pass
+    }
     {
         constexpr int RL = P::RL, ML = P::ML;
         // running first-strict-maximum exactly as fft.java:201-211: m starts at
@@ -510,6 +563,10 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
             }
         }
     }
+    if constexpr (!P::PERSIST) break;
+    __syncthreads();                             // shared memory and s_max/s_idx are reused by the next block
+    blk0 += blk_step;
+    } while (blk0 < a.nblocks);
 }
 
 }  // namespace fft
