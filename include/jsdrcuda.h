@@ -22,6 +22,9 @@
  *     (IAudioHandler.java:3-5, nominal +-1); int16 IQ is the IRawHandler
  *     contract (IRawHandler.java:3-5, s16le, before I/Q correction), converted
  *     on the device by the rule of JavaAudio.java:276-293.
+ *   - threading: a context and the handles created from it are driven by one thread at a
+ *     time, like the reference's handlers, which all run on JavaAudio's single "run" thread
+ *     (JavaAudio.java:298-304).  Different contexts (one per GPU) are independent.
  *   - there is no CPU fallback: without a CUDA device every create call fails
  *     with JSDR_ECUDA.
  */

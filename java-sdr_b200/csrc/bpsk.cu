@@ -851,11 +851,9 @@ int launch_stream_w(jsdr_bpsk *b, const stream::Params &sp)
     jsdr_ctx *ctx = b->ctx;
     auto kern = stream::k_mixdecim_stream<PREC, NTAPS, DD, W>;
     constexpr size_t smem = stream::smem_bytes<W, DD>();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     const int warps = sp.ncw * sp.nseg;
     const int grid = std::min((warps + W - 1) / W, sp.grid);
     ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);

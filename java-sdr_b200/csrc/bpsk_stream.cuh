@@ -64,6 +64,12 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(u64_of(a)), "l"(u64_of(b)), "l"(u64_of(c)));
     return f2_of(r);
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(u64_of(a)), "l"(u64_of(b)));
+    return f2_of(r);
+}
 __device__ __forceinline__ float2 mul2(float2 a, float2 b)
 {
     unsigned long long r;
@@ -166,11 +172,21 @@ __device__ __forceinline__ void period_body(const Params &p, const uint32_t *myr
             }
         }
         w ^= 0x80008000u;              // exact s16 -> float: splice into the mantissa of 2^23
-        const float fi = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)) - 8421376.0f;
-        const float fq = __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)) - 8421376.0f;
+        // (I, Q) as one packed pair: the bias subtraction and the division below are one FADD2 /
+        // FMUL2 / FFMA2 each for both halves
+        const float2 f2 = add2(make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
+                                           __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432))),
+                               make_float2(-8421376.0f, -8421376.0f));
+        const float fi = f2.x, fq = f2.y;
         if constexpr (PREC == PREC_F64) {
-            const double xi = (double)s16_over_32767(fi);      // JavaAudio.java:283
-            const double xq = (double)s16_over_32767(fq);
+            // (float)s / 32767f, correctly rounded (JavaAudio.java:283): q0 = s*r, e = fma(-q0, 32767, s),
+            // q = fma(r, e, q0) with r = fl(1/32767) — s16_over_32767 of bpsk.cu on both halves at once
+            const float2 r2 = make_float2(3.0518509447574615e-05f, 3.0518509447574615e-05f);
+            const float2 q0 = mul2(f2, r2);
+            const float2 e2 = fma2(q0, make_float2(-32767.0f, -32767.0f), f2);
+            const float2 q2 = fma2(r2, e2, q0);
+            const double xi = (double)q2.x;
+            const double xq = (double)q2.y;
             const double2 cs = lds_d2(taddr[j]);
             double mi = __dmul_rn(xi, cs.x);   // :389-390 i*cosTab[ix], q*sinTab[ix]
             double mq = __dmul_rn(xq, cs.y);

@@ -67,6 +67,21 @@ struct jsdr_ctx {
 
 namespace jsdr {
 
+// Function attributes (dynamic shared memory limits, occupancy) are per device: state kept by
+// a launch site is indexed by the context's device, so that contexts on different GPUs of one
+// process each set their own.
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlag {
+    bool done[kMaxDevices] = {false};
+    bool test_and_set(int dev)
+    {
+        if (dev < 0 || dev >= kMaxDevices) return false;   // unknown device: redo every time
+        const bool was = done[dev];
+        done[dev] = true;
+        return was;
+    }
+};
+
 // Check the launch that was just made and count it.
 static inline int launched(jsdr_ctx *ctx, const char *what)
 {

@@ -468,11 +468,9 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
         JSDR_TRY(launched(ctx, "k_sync"));
     }
     const size_t smem = sizeof(fec::DecodeSmem);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr_done;
+    if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(fec::k_fec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
     fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->stream>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
                                                                f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan);
     JSDR_TRY(launched(ctx, "k_fec_decode"));

@@ -11,22 +11,19 @@ namespace fft {
 template <class P, int IN, int OUT>
 static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
 {
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done;
     auto kern = fft_kernel<P, IN, OUT>;
-    if (!attr_done) {
+    if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-        attr_done = true;
-    }
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
     if constexpr (P::PERSIST) {   // resident CTAs loop over the blocks
-        static int resident = 0;
-        if (!resident) {
-            int per_sm = 0;
+        static int per_sm = 0;                    // a property of the kernel and sm_100a, not of the device index
+        if (!per_sm) {
             JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, P::SMEM));
-            resident = std::max(1, per_sm) * ctx->sm_count;
+            per_sm = std::max(1, per_sm);
         }
-        grid = std::min(grid, resident);
+        grid = std::min(grid, per_sm * ctx->sm_count);
     }
     ProfScope prof(ctx, JSDR_K_FFT, st);
     kern<<<grid, P::T, P::SMEM, st>>>(a);
