@@ -576,38 +576,96 @@ __device__ __forceinline__ double2 vco_mix(const DmParams &p, const double *sTab
     return make_double2(__dmul_rn(d.x, sTab[ix]), __dmul_rn(d.y, sTab[256 + ix]));
 }
 
-__global__ void __launch_bounds__(2 * kDmTile) k_matched(const DmParams p)
+// One CTA = one channel x 2080 outputs, five warps.  Lane t of warp w computes the 13 outputs
+// 65t + 13w .. 65t + 13w + 12 of the tile.  The reference sums by buffer slot
+// (:519-523): output m visits ages a0, a0+1, .., 64, 0, .., a0-1 with a0 = (m + 1 + calls before
+// this block) mod 65, tap = dmFilter[age], sample = v[m - age].  For 13 consecutive outputs the
+// age at step n is c + r (c = a0 + n mod 65, r = 0..12): the same sample v[m0 - c] serves every
+// output that has not wrapped yet (tap dmFilter[c + r]) and v[m0 - c + 65] those that have.  So
+// a step is two 16-byte loads for 52 multiply-adds, and because the threads of a warp are 65
+// outputs apart, a0 — and with it the set of steps where some outputs have wrapped — is the same
+// for all of them: no divergence, and the taps are warp-uniform (shared-memory broadcast).
+// Every output still accumulates in the reference's order, so the result is bit-identical.
+constexpr int kDm2R = 13;                                 // outputs per thread
+constexpr int kDm2Warps = 65 / kDm2R;                     // warp w computes outputs 13w .. 13w+12 of every 65
+constexpr int kDm2Threads = 32 * kDm2Warps;
+constexpr int kDm2Tile = 32 * 65;                         // 2080 outputs per CTA
+
+__global__ void __launch_bounds__(kDm2Threads) k_matched(const DmParams p)
 {
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    double2 *sV = reinterpret_cast<double2 *>(dm_smem);              // VCO-mixed samples, tile index i <-> m = m0 - 64 + i
     __shared__ double sTab[512];
-    __shared__ double sH[kDmTaps];
-    __shared__ double vI[kDmTile + 64], vQ[kDmTile + 64];
+    __shared__ double sT2[2 * kDmTaps];                              // dmFilter twice back to back (:58-67)
     const int tid = threadIdx.x, ch = blockIdx.y;
-    const int m0 = blockIdx.x * kDmTile;
-    const int cnt = min(kDmTile, p.NO - m0);
-    for (int i = tid; i < 512; i += blockDim.x) sTab[i] = p.cossin[i];
-    for (int i = tid; i < kDmTaps; i += blockDim.x) sH[i] = p.dmtaps[i];
+    const int m0 = blockIdx.x * kDm2Tile;
+    const int cnt = min(kDm2Tile, p.NO - m0);
+    for (int i = tid; i < 512; i += kDm2Threads) sTab[i] = p.cossin[i];
+    for (int i = tid; i < 2 * kDmTaps; i += kDm2Threads) sT2[i] = p.dmtaps[i % kDmTaps];
     __syncthreads();
-    for (int ii = tid; ii < cnt + 64; ii += blockDim.x) {
-        int m = m0 - 64 + ii;
-        double2 v = (m < 0) ? p.hist_in[(size_t)ch * 64 + 64 + m] : vco_mix(p, sTab, ch, m);
-        vI[ii] = v.x;
-        vQ[ii] = v.y;
+    // staging: 8 loads in flight per thread (one warp per CTA: the latency has to be covered here)
+    for (int i0 = 0; i0 < kDm2Tile + 64; i0 += 8 * kDm2Threads) {
+        double2 d[8];
+        int ix[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int ii = i0 + u * kDm2Threads + tid, m = m0 - 64 + ii;
+            d[u] = make_double2(0.0, 0.0);
+            ix[u] = -1;
+            if (ii < kDm2Tile + 64) {
+                if (m < 0) d[u] = p.hist_in[(size_t)ch * 64 + 64 + m];
+                else if (m < p.NO) {
+                    d[u] = p.ds[(size_t)ch * p.max_ds + m];
+                    ix[u] = p.vco_ix[m];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int ii = i0 + u * kDm2Threads + tid;
+            if (ii < kDm2Tile + 64) {
+                double2 v = d[u];
+                if (ix[u] >= 0) v = make_double2(__dmul_rn(v.x, sTab[ix[u]]), __dmul_rn(v.y, sTab[256 + ix[u]]));   // :515-516
+                sV[ii] = v;
+            }
+        }
     }
     __syncthreads();
-    const int lo = tid & (kDmTile - 1), comp = tid / kDmTile;
-    if (lo < cnt) {
-        // :519-523 sums by buffer slot: ages a0, a0+1, .., 64, 0, .., a0-1 with
-        // a0 = (calls so far + 1) mod 65
-        const double *vX = comp ? vQ : vI;
-        int age = (p.base65 + m0 + lo + 1) % 65;
-        const int top = lo + 64;
-        double acc = 0.0;
+    {
+        const int lo = 65 * (tid & 31) + kDm2R * (tid >> 5);         // first of this thread's 13 outputs (tile local)
+        if (lo >= cnt) return;
+        const int a0 = (p.base65 + m0 + lo + 1) % 65;                // uniform across the warp (lanes are 65 outputs apart)
+        double ai[kDm2R], aq[kDm2R];
+#pragma unroll
+        for (int r = 0; r < kDm2R; r++) ai[r] = aq[r] = 0.0;
+        const double2 *vb = sV + lo + 64;                            // v[m] of output lo
+#pragma unroll 1
         for (int n = 0; n < kDmTaps; n++) {
-            acc = __dadd_rn(acc, __dmul_rn(vX[top - age], sH[age]));
-            if (++age == 65) age = 0;
+            int c = a0 + n;
+            if (c >= 65) c -= 65;
+            const double2 xa = vb[-c];
+            const double *h = sT2 + c;
+            if (c + kDm2R - 1 < 65) {                                // nobody has wrapped: one sample for all
+#pragma unroll
+                for (int r = 0; r < kDm2R; r++) {
+                    ai[r] = __dadd_rn(ai[r], __dmul_rn(xa.x, h[r]));
+                    aq[r] = __dadd_rn(aq[r], __dmul_rn(xa.y, h[r]));
+                }
+            } else {
+                const double2 xb = vb[65 - c];                       // (needs c >= 53: index <= lo + 76, staged)
+#pragma unroll
+                for (int r = 0; r < kDm2R; r++) {
+                    const bool w = c + r >= 65;
+                    const double xi = w ? xb.x : xa.x, xq = w ? xb.y : xa.y;
+                    ai[r] = __dadd_rn(ai[r], __dmul_rn(xi, h[r]));
+                    aq[r] = __dadd_rn(aq[r], __dmul_rn(xq, h[r]));
+                }
+            }
         }
-        double *o = reinterpret_cast<double *>(p.dm_out + (size_t)ch * p.max_ds + m0 + lo);
-        o[comp] = acc;
+        double2 *o = p.dm_out + (size_t)ch * p.max_ds + m0 + lo;
+#pragma unroll
+        for (int r = 0; r < kDm2R; r++)
+            if (lo + r < cnt) o[r] = make_double2(ai[r], aq[r]);
     }
 }
 
@@ -1125,10 +1183,14 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         dp.cossin = b->d_cossin;
         dp.base65 = (int)(b->cnt_ds % 65);
         dp.dm_out = b->d_dm_out;
-        dim3 grid((NO + kDmTile - 1) / kDmTile, nchan);
+        dim3 grid((NO + kDm2Tile - 1) / kDm2Tile, nchan);
+        const size_t dm_smem = sizeof(double2) * (size_t)(kDm2Tile + 64 + 16);
+        static PerDeviceFlag dm_attr;
+        if (!dm_attr.test_and_set(ctx->device))
+            JSDR_CUDA(cudaFuncSetAttribute(k_matched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm_smem));
         {
             ProfScope prof(ctx, JSDR_K_MATCHED, ctx->stream);
-            k_matched<<<grid, 2 * kDmTile, 0, ctx->stream>>>(dp);
+            k_matched<<<grid, kDm2Threads, dm_smem, ctx->stream>>>(dp);
         }
         JSDR_TRY(launched(ctx, "k_matched"));
         k_dm_tail<<<nchan, 64, 0, ctx->stream>>>(dp);
