@@ -63,6 +63,8 @@ def test_frames_payload_and_error_counts(ctx, ebn0):
     assert not [g for g in got if g[0] == 1 and g[2] >= 0]       # the off-signal tuner decodes nothing
     cfec, cdec = bank.fec_counters()
     assert cfec[0] == len(ref) and cdec[0] == len(good)
+    bank.receive(np.zeros(0, np.float32))                        # an empty block publishes no (stale) frames
+    assert bank.read_frames() == []
     bank.close()
 
 
