@@ -59,6 +59,31 @@ public final class JsdrCuda {
 	static final MethodHandle BPSK_READ_COUNTERS = h("jsdr_bpsk_read_counters",
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
 
+	static final MethodHandle BPSK_SET_AUTOTUNE = h("jsdr_bpsk_set_autotune",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));             // "FUNcube<i>-bpsk-dofft" / "-upper"
+	static final MethodHandle BPSK_READ_CENTRE = h("jsdr_bpsk_read_centre",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	static final MethodHandle BPSK_SET_PRECISION = h("jsdr_bpsk_set_precision",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+	// frame stage: the sync correlator and FECDecoder.FECDecode on the device; mettab is
+	// FECDecoder's own metric table (FECDecoder.java:67-100) flattened to short[512]
+	static final MethodHandle BPSK_ENABLE_FEC = h("jsdr_bpsk_enable_fec",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle BPSK_READ_FRAMES = h("jsdr_bpsk_read_frames",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
+	// demod.java: FIR + NCO + detector + AGC + s16 audio in one call
+	static final MethodHandle DEMOD_CREATE = h("jsdr_demod_create",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+	static final MethodHandle DEMOD_WEIGHTS = h("jsdr_demod_weights",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT));
+	static final MethodHandle DEMOD_SET_MODE = h("jsdr_demod_set_mode",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+	static final MethodHandle DEMOD_RECEIVE_AUDIO = h("jsdr_demod_receive_audio_f32",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT));
+	// waterfall.java: paintLine on the device (chained behind the fft handler's PSD)
+	static final MethodHandle WATERFALL_ROWS = h("jsdr_waterfall_rows",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT));
+
 	/** Status code to message; never throws out of a handler (JavaAudio.java:321-323). */
 	static String check(int rc) {
 		if (rc == 0) return null;
