@@ -903,12 +903,13 @@ int bpsk_reset_ds(jsdr_bpsk *b)
 }
 
 // The streaming tuner + decimator: one lane per channel, one warp per segment of R outputs.
-template <int PREC, int NTAPS, int DD, int W>
-int launch_stream_w(jsdr_bpsk *b, const stream::Params &sp)
+template <int FMT, int PREC, int NTAPS, int DD>
+int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
 {
     jsdr_ctx *ctx = b->ctx;
-    auto kern = stream::k_mixdecim_stream<PREC, NTAPS, DD, W>;
-    constexpr size_t smem = stream::smem_bytes<W, DD>();
+    constexpr int W = (FMT == FMT_S16) ? stream::kWarps : stream::kWarpsF32;
+    auto kern = stream::k_mixdecim_stream<FMT, PREC, NTAPS, DD, W>;
+    constexpr size_t smem = stream::smem_bytes<FMT, W, DD>();
     static PerDeviceFlag attr_done;
     if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -919,29 +920,11 @@ int launch_stream_w(jsdr_bpsk *b, const stream::Params &sp)
     return launched(ctx, "k_mixdecim_stream");
 }
 
-static int pump_concurrent()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("JSDR_PUMP_CONCURRENT");      // (tuning aid)
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
-
-// Whole-SM CTAs (15 warps) normally; 8-warp CTAs when the pump runs the FFT beside the decimator,
-// so that FFT CTAs fit on the same SM.
-template <int PREC, int NTAPS, int DD>
-int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
-{
-    if (sp.warps_per_cta == stream::kWarpsShared) return launch_stream_w<PREC, NTAPS, DD, stream::kWarpsShared>(b, sp);
-    return launch_stream_w<PREC, NTAPS, DD, stream::kWarps>(b, sp);
-}
-
+template <int FMT>
 int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
 {
     stream::Params sp;
-    sp.in = reinterpret_cast<const uint32_t *>(mp.in);
+    sp.in = mp.in;
     sp.chan_stride = mp.chan_stride;
     sp.S = S;
     sp.ic = mp.ic;
@@ -961,7 +944,7 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     // about three per resident warp, their count chosen so that the last wave is full.
     const int scout_ctas = (mp.nchan + scout_threads() - 1) / scout_threads();
     sp.grid = std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
-    sp.warps_per_cta = (b->share_sm && pump_concurrent()) ? stream::kWarpsShared : stream::kWarps;
+    sp.warps_per_cta = (FMT == FMT_S16) ? stream::kWarps : stream::kWarpsF32;
     const int resident = sp.grid * sp.warps_per_cta;
     int nseg = std::max(1, 3 * resident / sp.ncw);
     int R = (mp.NO + nseg - 1) / nseg;
@@ -976,10 +959,10 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     }
     const bool f32 = b->precision == JSDR_PREC_F32;
     if (b->ntaps == 27 && mp.D == 10)
-        return f32 ? launch_stream_shape<stream::PREC_F32, 27, 10>(b, sp) : launch_stream_shape<stream::PREC_F64, 27, 10>(b, sp);
+        return f32 ? launch_stream_shape<FMT, stream::PREC_F32, 27, 10>(b, sp) : launch_stream_shape<FMT, stream::PREC_F64, 27, 10>(b, sp);
     if (b->ntaps == 27 && mp.D == 20)
-        return f32 ? launch_stream_shape<stream::PREC_F32, 27, 20>(b, sp) : launch_stream_shape<stream::PREC_F64, 27, 20>(b, sp);
-    return f32 ? launch_stream_shape<stream::PREC_F32, 64, 20>(b, sp) : launch_stream_shape<stream::PREC_F64, 64, 20>(b, sp);
+        return f32 ? launch_stream_shape<FMT, stream::PREC_F32, 27, 20>(b, sp) : launch_stream_shape<FMT, stream::PREC_F64, 27, 20>(b, sp);
+    return f32 ? launch_stream_shape<FMT, stream::PREC_F32, 64, 20>(b, sp) : launch_stream_shape<FMT, stream::PREC_F64, 64, 20>(b, sp);
 }
 
 // doBufferFFT (:406-464) for every channel of the bank: binary64 forward transform, search,
@@ -1122,13 +1105,13 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         }
     }
     bool streamed = false;
-    if (NO > 0 && FMT == FMT_S16 && b->kernel_mode != JSDR_KERNEL_TILE) {
+    if (NO > 0 && b->kernel_mode != JSDR_KERNEL_TILE) {
         // many channels: the streaming kernel (bpsk_stream.cuh); needs a compiled (taps, D) shape
         const bool shape_ok = (b->ntaps == 27 && D == 10) || (b->ntaps == 27 && D == 20) || (b->ntaps == 64 && D == 20);
         const bool want = b->kernel_mode == JSDR_KERNEL_STREAM || (nchan >= 32 && NO >= 64) ||
                           (b->precision == JSDR_PREC_F32 && nchan >= 8);
         if (shape_ok && want) {
-            JSDR_TRY(launch_stream(b, mp, P.S));
+            JSDR_TRY(launch_stream<FMT>(b, mp, P.S));
             streamed = true;
         }
     }
@@ -1510,14 +1493,7 @@ int pump_fft(void *user, const void *d_in)
 {
     PumpJob *j = static_cast<PumpJob *>(user);
     jsdr_ctx *ctx = j->f->ctx;
-    if (!pump_concurrent())
-        return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream);
-    // beside the decimator: fork to the low-priority auxiliary stream; the caller joins
-    JSDR_CUDA(cudaEventRecord(ctx->ev_aux_fork, ctx->stream));
-    JSDR_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_aux_fork, 0));
-    JSDR_TRY(fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->aux));
-    JSDR_CUDA(cudaEventRecord(ctx->ev_aux_join, ctx->aux));
-    return JSDR_OK;
+    return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream);
 }
 }  // namespace
 
@@ -1544,11 +1520,7 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     if (mem == JSDR_MEM_DEVICE) {
         job.d_psd = psd;
         job.d_peak = peak_bin;
-        b->share_sm = 1;
-        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
-        b->share_sm = 0;
-        if (rc == JSDR_OK && pump_concurrent()) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux_join, 0));
-        return rc;
+        return bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
     }
     if (f->out_cap < psd_elems * sizeof(float)) {
         cudaFree(f->d_out);

@@ -32,13 +32,13 @@ namespace jsdr {
 namespace bpsk {
 namespace stream {
 
-constexpr int kWarps = 15;
-constexpr int kWarpsShared = 8;       // CTA size when another kernel's CTAs share the SM
+constexpr int kWarps = 15;            // s16 input: 15 warps (one CTA per SM)
+constexpr int kWarpsF32 = 8;          // float input: the ring rows are twice as wide
 constexpr int kMaxTaps = 64;
 enum { PREC_F64 = 0, PREC_F32 = 1 };
 
 struct Params {
-    const uint32_t *in;                 // [nchan][chan_stride] s16 IQ pairs
+    const void *in;                     // [nchan][chan_stride] s16 IQ pairs (uint32) or float IQ pairs (float2)
     long long chan_stride;
     int S, ic, qc;
     const unsigned long long *tu_dx56;  // [nchan] index step per sample, 8.56 fixed point; 0: exact replay only
@@ -49,7 +49,7 @@ struct Params {
     const double2 *cossin;              // [257] (cos, sin); entry 256 = (1, 1), the mixer bypass
     int n0, NO, R, nseg, ncw;           // first output's sample, outputs, outputs per segment, segments, channel groups
     int grid;                           // CTAs to launch (host side only)
-    int warps_per_cta;                  // kWarps or kWarpsShared (host side only)
+    int warps_per_cta;                  // kWarps or kWarpsF32 (host side only)
     double2 *ds_out;
     int max_ds;
     double taps[kMaxTaps];
@@ -117,18 +117,28 @@ struct Acc<PREC_F32> {
     __device__ __forceinline__ void zero() { i = 0.f; q = 0.f; }
 };
 
-constexpr int kRing = 64;                 // samples per row in the ring: two 32-sample chunks
+// The raw element the ring holds: one s16 I/Q pair (IRawHandler bytes) or one float I/Q pair
+// (IAudioHandler floats).  A staging piece is 16 bytes (4 or 2 samples), a chunk is 8 pieces
+// (128 bytes per row: 32 or 16 samples), so the staging code is the same for both.
+template <int FMT> struct Raw;
+template <> struct Raw<FMT_S16> { typedef uint32_t type; };
+template <> struct Raw<FMT_F32> { typedef float2 type; };
+template <int FMT> __host__ __device__ constexpr int raw_words() { return FMT == FMT_S16 ? 1 : 2; }   // 32-bit words per sample
+template <int FMT> __host__ __device__ constexpr int piece_samples() { return 4 / raw_words<FMT>(); }
+template <int FMT> __host__ __device__ constexpr int chunk_samples() { return 8 * piece_samples<FMT>(); }
+
+constexpr int kRing = 64;                 // samples per row in the ring: two (s16) or four (float) chunks
 // The first D (rounded up to 4) positions of the ring are mirrored behind its end, so that a
 // period that would wrap can be read at fixed offsets below position p+64 instead.
 template <int DD> __host__ __device__ constexpr int mirror_len() { return (DD + 3) & ~3; }
-template <int DD> __host__ __device__ constexpr int row_pitch() { return (kRing + mirror_len<DD>()) | 1; }   // odd (words): no bank conflicts
+template <int DD> __host__ __device__ constexpr int row_pitch() { return (kRing + mirror_len<DD>()) | 1; }   // odd (samples): no bank conflicts
 constexpr int kScratch = 24;              // uint16 per lane for the exact-replay path (>= D)
 constexpr int kTabBytes = 257 * 128;      // 8 x double2 or 16 x float2 copies of each of the 257 entries
 
-template <int W, int DD>
+template <int FMT, int W, int DD>
 constexpr size_t smem_bytes()
 {
-    return (size_t)kTabBytes + (size_t)W * (32 * row_pitch<DD>() * 4 + 32 * kScratch * 2);
+    return (size_t)kTabBytes + (size_t)W * (32 * row_pitch<DD>() * 4 * raw_words<FMT>() + 32 * kScratch * 2);
 }
 
 __device__ __forceinline__ double2 lds_d2(unsigned addr)
@@ -149,44 +159,58 @@ __device__ __forceinline__ float2 lds_f2(unsigned addr)
 // is a sample of this call (not history), the period does not wrap in the ring and
 // there is no I/Q correction, so the reads are at fixed offsets below `top`;
 // otherwise each sample checks for itself.
-template <int PREC, int NTAPS, int DD, bool FAST>
-__device__ __forceinline__ void period_body(const Params &p, const uint32_t *myrow, const unsigned (&taddr)[DD], int s_hi,
-                                            int ch, Acc<PREC> (&acc)[(NTAPS + DD - 1) / DD])
+template <int FMT, int PREC, int NTAPS, int DD, bool FAST>
+__device__ __forceinline__ void period_body(const Params &p, const typename Raw<FMT>::type *myrow,
+                                            const unsigned (&taddr)[DD], int s_hi, int ch,
+                                            Acc<PREC> (&acc)[(NTAPS + DD - 1) / DD])
 {
+    typedef typename Raw<FMT>::type raw_t;
     constexpr int NQ = (NTAPS + DD - 1) / DD;
     constexpr int H = NTAPS - 1;
     const int ptop = s_hi & (kRing - 1);
-    const uint32_t *top = myrow + (ptop >= DD - 1 ? ptop : ptop + kRing);   // wrapping periods read the mirror
+    const raw_t *top = myrow + (ptop >= DD - 1 ? ptop : ptop + kRing);   // wrapping periods read the mirror
 #pragma unroll
     for (int j = 0; j < DD; j++) {
         const int s = s_hi - j;
         bool hist = false;
-        uint32_t w = 0;
+        raw_t rw = raw_t();
         if constexpr (FAST) {
-            w = top[-j];
+            rw = top[-j];
         } else {
             hist = s < 0;
-            if (!hist) {
-                w = myrow[s & (kRing - 1)];
-                w = (((w & 0xffffu) + (unsigned)p.ic) & 0xffffu) | ((((w >> 16) + (unsigned)p.qc) & 0xffffu) << 16);
-            }
+            if (!hist) rw = myrow[s & (kRing - 1)];
         }
-        w ^= 0x80008000u;              // exact s16 -> float: splice into the mantissa of 2^23
-        // (I, Q) as one packed pair: the bias subtraction and the division below are one FADD2 /
-        // FMUL2 / FFMA2 each for both halves
-        const float2 f2 = add2(make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
-                                           __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432))),
-                               make_float2(-8421376.0f, -8421376.0f));
+        // f2 = (I, Q) as floats: the s16 values themselves (the 1/32767 comes below), or the floats
+        float2 f2;
+        if constexpr (FMT == FMT_S16) {
+            uint32_t w = rw;
+            if constexpr (!FAST)
+                w = (((w & 0xffffu) + (unsigned)p.ic) & 0xffffu) | ((((w >> 16) + (unsigned)p.qc) & 0xffffu) << 16);
+            w ^= 0x80008000u;          // exact s16 -> float: splice into the mantissa of 2^23
+            // (I, Q) as one packed pair: the bias subtraction and the division below are one FADD2 /
+            // FMUL2 / FFMA2 each for both halves
+            f2 = add2(make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
+                                  __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432))),
+                      make_float2(-8421376.0f, -8421376.0f));
+        } else {
+            f2 = rw;
+        }
         const float fi = f2.x, fq = f2.y;
         if constexpr (PREC == PREC_F64) {
-            // (float)s / 32767f, correctly rounded (JavaAudio.java:283): q0 = s*r, e = fma(-q0, 32767, s),
-            // q = fma(r, e, q0) with r = fl(1/32767) — s16_over_32767 of bpsk.cu on both halves at once
-            const float2 r2 = make_float2(3.0518509447574615e-05f, 3.0518509447574615e-05f);
-            const float2 q0 = mul2(f2, r2);
-            const float2 e2 = fma2(q0, make_float2(-32767.0f, -32767.0f), f2);
-            const float2 q2 = fma2(r2, e2, q0);
-            const double xi = (double)q2.x;
-            const double xq = (double)q2.y;
+            double xi, xq;
+            if constexpr (FMT == FMT_S16) {
+                // (float)s / 32767f, correctly rounded (JavaAudio.java:283): q0 = s*r, e = fma(-q0, 32767, s),
+                // q = fma(r, e, q0) with r = fl(1/32767) — s16_over_32767 of bpsk.cu on both halves at once
+                const float2 r2 = make_float2(3.0518509447574615e-05f, 3.0518509447574615e-05f);
+                const float2 q0 = mul2(f2, r2);
+                const float2 e2 = fma2(q0, make_float2(-32767.0f, -32767.0f), f2);
+                const float2 q2 = fma2(r2, e2, q0);
+                xi = (double)q2.x;
+                xq = (double)q2.y;
+            } else {
+                xi = (double)fi;       // :372-373 (double)buf[n*2]
+                xq = (double)fq;
+            }
             const double2 cs = lds_d2(taddr[j]);
             double mi = __dmul_rn(xi, cs.x);   // :389-390 i*cosTab[ix], q*sinTab[ix]
             double mq = __dmul_rn(xq, cs.y);
@@ -228,13 +252,18 @@ __device__ __forceinline__ void period_body(const Params &p, const uint32_t *myr
     }
 }
 
-template <int PREC, int NTAPS, int DD, int W>
-__global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(const Params p)
+template <int FMT, int PREC, int NTAPS, int DD, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
 {
+    typedef typename Raw<FMT>::type raw_t;
     constexpr int NQ = (NTAPS + DD - 1) / DD;          // live outputs per sample
-    constexpr int kPitch = row_pitch<DD>();
+    constexpr int kPitch = row_pitch<DD>();            // samples
     constexpr int MIR = mirror_len<DD>();
-    constexpr int WARP_BYTES = 32 * kPitch * 4 + 32 * kScratch * 2;
+    constexpr int SPP = piece_samples<FMT>();          // samples per 16-byte staging piece
+    constexpr int CH = chunk_samples<FMT>();           // samples per staged chunk (128 bytes per row)
+    constexpr int CHLOG = (CH == 32) ? 5 : 4;
+    constexpr int NSLOT = kRing / CH;
+    constexpr int WARP_BYTES = 32 * kPitch * (int)sizeof(raw_t) + 32 * kScratch * 2;
     static_assert(DD <= kScratch && DD <= 32, "period");
     static_assert(NTAPS <= kMaxTaps && NQ <= 4, "taps");
 
@@ -247,25 +276,26 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
         for (int i = tid; i < 257 * 8; i += W * 32) tab[i] = p.cossin[i >> 3];
     } else {
         float2 *tab = reinterpret_cast<float2 *>(smem);
+        // s16 input: the 1/32767 of the conversion (JavaAudio.java:283) is folded into the table
+        const double scale = (FMT == FMT_S16) ? 32767.0 : 1.0;
         for (int i = tid; i < 257 * 16; i += W * 32) {
             const double2 cs = p.cossin[i >> 4];
-            // the 1/32767 of the s16 conversion (JavaAudio.java:283) folded into the table
-            tab[i] = make_float2((float)(cs.x / 32767.0), (float)(cs.y / 32767.0));
+            tab[i] = make_float2((float)(cs.x / scale), (float)(cs.y / scale));
         }
     }
     __syncthreads();
     // shared-window address of this lane's copy of table entry 0 (128-byte aligned base: the index is or-ed in)
     const unsigned lane_tab = (unsigned)__cvta_generic_to_shared(smem) + ((PREC == PREC_F64) ? (lane & 7) * 16 : (lane & 15) * 8);
 
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kTabBytes + warp * WARP_BYTES);
-    uint16_t *scratch = reinterpret_cast<uint16_t *>(smem + kTabBytes + warp * WARP_BYTES + 32 * kPitch * 4) + lane * kScratch;
-    const uint32_t *myrow = ring + lane * kPitch;
+    raw_t *ring = reinterpret_cast<raw_t *>(smem + kTabBytes + warp * WARP_BYTES);
+    uint16_t *scratch = reinterpret_cast<uint16_t *>(smem + kTabBytes + warp * WARP_BYTES + 32 * kPitch * (int)sizeof(raw_t)) + lane * kScratch;
+    const raw_t *myrow = ring + lane * kPitch;
 
-    // staging role of this lane: rows 4i + (lane>>3), 16-byte piece (lane&7) of a 32-sample chunk
+    // staging role of this lane: rows 4i + (lane>>3), 16-byte piece (lane&7) of a chunk
     const int srow = lane >> 3, spiece = lane & 7;
     const long long stride4 = 4 * p.chan_stride;       // samples between this lane's consecutive staging rows
-    const bool aligned = ((reinterpret_cast<size_t>(p.in) & 15) == 0) && ((p.chan_stride & 3) == 0);
-    const bool iqcorr = (p.ic | p.qc) != 0;
+    const bool aligned = ((reinterpret_cast<size_t>(p.in) & 15) == 0) && ((p.chan_stride * (long long)sizeof(raw_t)) % 16 == 0);
+    const bool iqcorr = FMT == FMT_S16 && (p.ic | p.qc) != 0;
 
     for (int wg = blockIdx.x * W + warp; wg < p.ncw * p.nseg; wg += gridDim.x * W) {
         const int cw = wg % p.ncw, seg = wg / p.ncw;
@@ -278,14 +308,14 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
         const int nper = p.R + NQ - 1;
         const unsigned long long dx = p.tu_dx56[ch];
         const bool exact_lane = (dx == 0ull);
-        const uint32_t *stage0 = p.in + (long long)(ch0 + srow) * p.chan_stride + spiece * 4;
+        const raw_t *stage0 = reinterpret_cast<const raw_t *>(p.in) + (long long)(ch0 + srow) * p.chan_stride + spiece * SPP;
 
-        // ---- staging: chunk c = samples [32c, 32c+32) of 32 rows -> ring slot c&1
+        // ---- staging: chunk c = samples [CH*c, CH*c+CH) of 32 rows -> ring slot c mod NSLOT
         uint4 pre[8];
         auto load_chunk = [&](int c) {
-            const int s0 = c * 32 + spiece * 4;
-            if (c >= 0 && aligned && c * 32 + 32 <= p.S && rows == 32) {
-                const uint32_t *src = stage0 + c * 32;
+            const int s0 = c * CH + spiece * SPP;
+            if (c >= 0 && aligned && c * CH + CH <= p.S && rows == 32) {
+                const raw_t *src = stage0 + c * CH;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     pre[i] = ldg_stream_u4(reinterpret_cast<const uint4 *>(src));
@@ -295,32 +325,44 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const bool rok = c >= 0 && (srow + 4 * i) < rows;
-                    const uint32_t *src = stage0 + (long long)i * stride4 + c * 32;
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(stage0 + (long long)i * stride4 + c * CH);
                     uint32_t v[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         v[e] = 0u;
-                        if (rok && s0 + e < p.S) v[e] = src[e];
+                        if (rok && s0 + e / raw_words<FMT>() < p.S) v[e] = src[e];
                     }
                     pre[i] = make_uint4(v[0], v[1], v[2], v[3]);
                 }
             }
         };
         auto store_chunk = [&](int c) {
-            uint32_t *dst = ring + srow * kPitch + (c & 1) * 32 + spiece * 4;
+            const int pos = (c & (NSLOT - 1)) * CH + spiece * SPP;      // ring position of this lane's piece
+            uint32_t *dst = reinterpret_cast<uint32_t *>(ring + srow * kPitch + pos);
+            constexpr int RW = 4 * kPitch * raw_words<FMT>();             // words between staging rows of one lane
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                dst[0] = pre[i].x;
-                dst[1] = pre[i].y;
-                dst[2] = pre[i].z;
-                dst[3] = pre[i].w;
-                if ((c & 1) == 0 && spiece * 4 < MIR) {        // mirror of ring positions 0 .. MIR-1
-                    dst[kRing + 0] = pre[i].x;
-                    dst[kRing + 1] = pre[i].y;
-                    dst[kRing + 2] = pre[i].z;
-                    dst[kRing + 3] = pre[i].w;
+                if constexpr (FMT == FMT_S16) {
+                    dst[0] = pre[i].x;
+                    dst[1] = pre[i].y;
+                    dst[2] = pre[i].z;
+                    dst[3] = pre[i].w;
+                    if (pos < MIR) {                               // mirror of ring positions 0 .. MIR-1
+                        dst[kRing + 0] = pre[i].x;
+                        dst[kRing + 1] = pre[i].y;
+                        dst[kRing + 2] = pre[i].z;
+                        dst[kRing + 3] = pre[i].w;
+                    }
+                } else {
+                    uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+                    d2[0] = make_uint2(pre[i].x, pre[i].y);
+                    d2[1] = make_uint2(pre[i].z, pre[i].w);
+                    if (pos < MIR) {
+                        d2[kRing + 0] = make_uint2(pre[i].x, pre[i].y);
+                        d2[kRing + 1] = make_uint2(pre[i].z, pre[i].w);
+                    }
                 }
-                dst += 4 * kPitch;
+                dst += RW;
             }
         };
 
@@ -336,7 +378,7 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
         unsigned long long x_top = 0;
         bool bad_anchor = false;
 
-        int staged_lo = (n_top >> 5) + 1;              // lowest chunk in the ring
+        int staged_lo = (n_top >> CHLOG) + 1;          // lowest chunk in the ring
         __syncwarp();                                  // (the previous segment's reads are done)
         load_chunk(staged_lo - 1);
         store_chunk(staged_lo - 1);
@@ -348,8 +390,8 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
         for (int tt = 0; tt < nper; tt++) {
             const int s_hi = n_top - tt * DD;          // newest sample of the period (uniform)
             const int s_lo = s_hi - DD + 1;
-            if ((s_lo >> 5) < staged_lo) {             // uniform: the period enters the next chunk down
-                __syncwarp();
+            while ((s_lo >> CHLOG) < staged_lo) {      // uniform: the period enters the next chunk(s) down
+                __syncwarp();                          // (twice in a row only when D > chunk: float input, D = 20)
                 store_chunk(staged_lo - 1);
                 staged_lo--;
                 load_chunk(staged_lo - 1);
@@ -385,8 +427,8 @@ __global__ void __launch_bounds__(W * 32, (W <= 8) ? 2 : 1) k_mixdecim_stream(co
             }
 
             // ---- convert, mix, accumulate
-            if (s_lo >= 0 && !iqcorr) period_body<PREC, NTAPS, DD, true>(p, myrow, taddr, s_hi, ch, acc);
-            else period_body<PREC, NTAPS, DD, false>(p, myrow, taddr, s_hi, ch, acc);
+            if (s_lo >= 0 && !iqcorr) period_body<FMT, PREC, NTAPS, DD, true>(p, myrow, taddr, s_hi, ch, acc);
+            else period_body<FMT, PREC, NTAPS, DD, false>(p, myrow, taddr, s_hi, ch, acc);
 
             // ---- the oldest role is complete: scale (:469,486), store, rotate
             const int r_out = tt - (NQ - 1);

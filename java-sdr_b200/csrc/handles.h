@@ -67,7 +67,6 @@ struct jsdr_bpsk {
     unsigned long long *d_tu_dx56 = nullptr; // [nchan] the same in 8.56 fixed point (streaming kernel)
     int precision = 0;               // JSDR_PREC_F64 (exact) or JSDR_PREC_F32 (decimator in binary32)
     int kernel_mode = 0;             // JSDR_KERNEL_AUTO / _TILE / _STREAM
-    int share_sm = 0;                // set by the pump while another kernel runs beside the decimator
     double *d_tu_phase0 = nullptr;   // [nchan] initial tuPhase (zeros)
     const double *d_tu_phase = nullptr;   // committed tuPhase: phase0 or the phase_end of the last plan used
     // Scout output ("plan") for one block.  Two of them: while the data kernels work

@@ -23,8 +23,9 @@ def make_bank(ctx, rate, tun, taps, kernel, prec=J.PREC_F64, max_block=None):
     return bank
 
 
+@pytest.mark.parametrize("fmt", ["s16", "f32"])
 @pytest.mark.parametrize("rate,ntaps", [(96000, 27), (192000, 27), (192000, 64)])
-def test_stream_bit_exact_vs_oracle_ragged_blocks(ctx, rate, ntaps):
+def test_stream_bit_exact_vs_oracle_ragged_blocks(ctx, rate, ntaps, fmt):
     """Every compiled (taps, D) shape, 37 channels (one full warp + a partial one),
     ragged block lengths so that the decimation phase, the history and the tuner
     checkpoints all carry across calls."""
@@ -38,11 +39,16 @@ def test_stream_bit_exact_vs_oracle_ragged_blocks(ctx, rate, ntaps):
     bank = make_bank(ctx, rate, tun, taps, J.KERNEL_STREAM, max_block=8192)
     orcs = [O.Bpsk(rate, t, ds_taps=taps, stages=1) for t in tun]
     for S in (4000, 1, 19, 8192, 777, 2561, 64, 3000):
-        raw = rng.integers(-32768, 32768, (nchan, 2 * S)).astype(np.int16)
-        bank.receive_raw(raw)
+        if fmt == "s16":                                   # IRawHandler bytes, converted on the device
+            raw = rng.integers(-32768, 32768, (nchan, 2 * S)).astype(np.int16)
+            bank.receive_raw(raw)
+            fin = [O.s16_to_float(raw[c]) for c in range(nchan)]
+        else:                                              # IAudioHandler floats
+            fin = rng.uniform(-1, 1, (nchan, 2 * S)).astype(np.float32)
+            bank.receive(fin)
         ds = bank.read_ds()
         for c, o in enumerate(orcs):
-            ref = o.receive(O.s16_to_float(raw[c]))["ds"]
+            ref = o.receive(fin[c])["ds"]
             assert ds[c].shape == ref.shape, (S, c)
             assert np.array_equal(ds[c], ref), (S, c)
     bank.close()
@@ -88,7 +94,7 @@ def test_stream_shared_stream_fans_out(ctx):
 
 @pytest.mark.parametrize("rate,ntaps", [(96000, 27), (192000, 64)])
 def test_stream_f32_within_tolerance(ctx, rate, ntaps):
-    """binary32 mix + FIR against the binary64 oracle: 1e-4 of full scale."""
+    """binary32 mix + FIR against the binary64 oracle: 1e-4 of full scale (s16 and float input)."""
     nchan, S = 64, 19200
     rng = np.random.default_rng(8)
     tun = rng.uniform(2000, rate * 0.45, nchan)
@@ -96,12 +102,16 @@ def test_stream_f32_within_tolerance(ctx, rate, ntaps):
     a = make_bank(ctx, rate, tun, taps, J.KERNEL_STREAM, prec=J.PREC_F32, max_block=S)
     orcs = [O.Bpsk(rate, t, ds_taps=taps, stages=1) for t in tun[:8]]
     worst = 0.0
-    for k in range(2):
+    for k in range(4):
         raw = rng.integers(-32768, 32768, (nchan, 2 * S)).astype(np.int16)
-        a.receive_raw(raw)
+        fin = O.s16_to_float(raw.ravel()).reshape(nchan, 2 * S)
+        if k < 2:
+            a.receive_raw(raw)
+        else:
+            a.receive(fin)
         ds = a.read_ds()
         for c, o in enumerate(orcs):
-            ref = o.receive(O.s16_to_float(raw[c]))["ds"]
+            ref = o.receive(fin[c])["ds"]
             worst = max(worst, float(np.max(np.abs(ds[c] - ref))) / FULL_SCALE)
     assert worst <= 1e-4, worst
     assert worst <= 2e-6, worst       # what binary32 actually achieves here

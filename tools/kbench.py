@@ -53,6 +53,22 @@ def mix(nchan=4096, S=131072, rate=192000, ntaps=64):
         print(f"mix {name:10s} nchan={nchan} S={S} taps={ntaps} D={D}: {ms:8.3f} ms  {nchan * S / ms / 1e3:9.1f} Msamples/s  "
               f"{gbs:7.1f} GB/s  frac {gbs / PEAK:.3f}", flush=True)
         bank.close()
+    # float input (IAudioHandler path), half the channels to keep the resident batch the same size
+    nf = nchan // 2
+    d_f = ctx.dev_alloc(nf * S * 8)
+    tf = (tile[:64].astype(np.float32) / 32767.0)
+    for c0 in range(0, nf, 64):
+        d_f.upload(tf[: min(64, nf - c0)], offset=c0 * S * 8)
+    for name, prec in (("stream f64", J.PREC_F64), ("stream f32", J.PREC_F32)):
+        bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate), tuning=tun[:nf], max_block=S, stages=1)
+        if taps is not None:
+            bank.set_ds_filter(taps)
+        bank.set_precision(prec)
+        ms = time_ms(ctx, lambda: bank.receive_dev(d_f, S, S, s16=False))
+        b = nf * S * 8 + nf * (S // D) * 16
+        print(f"mix {name:10s} FLOAT IN nchan={nf} S={S}: {ms:8.3f} ms  {nf * S / ms / 1e3:9.1f} Msamples/s  "
+              f"{b / ms / 1e6:7.1f} GB/s  frac {b / ms / 1e6 / PEAK:.3f}", flush=True)
+        bank.close()
     ctx.close()
 
 
