@@ -285,6 +285,15 @@ def main():
     other_ms = ctx.timer_stop_ms() / max(2, a.steps // 2)
     bank.set_precision(J.PREC_F32 if a.precision == "f32" else J.PREC_F64)
 
+    # ---- BASELINE config 4 on its own: NCO mix + 64-tap FIR decimation of every channel, no FFT
+    for _ in range(2):
+        bank.receive_dev(d_raw, S, S, s16=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(3):
+        bank.receive_dev(d_raw, S, S, s16=True)
+    mixonly_ms = ctx.timer_stop_ms() / 3
+
     # ---- the whole FUNcube chain to bits (27-tap decimator, matched filter, bit timing) on the
     # same resident batch, for the record: the reference's own receiver shape at 192 kS/s
     bank_c = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S, stages=3)
@@ -329,8 +338,8 @@ def main():
     if dist is not None:
         import torch
         dev = torch.device("cuda", local)
-    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms), launches = sharding.reduce_timing(
-        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms], launches)
+    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms), launches = sharding.reduce_timing(
+        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms], launches)
     launches = int(launches)
 
     if rank == 0:
@@ -379,6 +388,11 @@ def main():
             "variants": {"decimator_" + other: {"value": round(world * samples / (other_ms * 1e-3) / 1e6, 1),
                                                 "unit": "Msamples/s", "ms_per_step": round(other_ms, 4),
                                                 "note": "same pipeline with the tuner+decimator in %s" % other},
+                         "tuner_decimator_only": {"value": round(world * samples / (mixonly_ms * 1e-3) / 1e6, 1),
+                                                  "unit": "Msamples/s", "ms_per_step": round(mixonly_ms, 4),
+                                                  "frac_of_hbm_peak": round((samples * 4 + nout * 16) / (mixonly_ms * 1e-3) / 1e9 / peak, 4),
+                                                  "note": "BASELINE config 4 alone: NCO mix + %d-tap FIR decimate x%d (%s), "
+                                                          "4 + 16/D algorithmic bytes per sample" % (a.taps, D, a.precision)},
                          "funcube_chain_to_bits": {"value": round(world * samples / (chain_ms * 1e-3) / 1e6, 1),
                                                    "unit": "Msamples/s", "ms_per_step": round(chain_ms, 4),
                                                    "note": "tuner + 27-tap decimator + 65-tap matched filter + bit timing "

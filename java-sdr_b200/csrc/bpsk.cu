@@ -155,15 +155,22 @@ __device__ __forceinline__ double phase_step2(double p, double inc, double th1, 
 
 constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
 
-static int scout_threads()
+// CTA size of the phase scout = how many SMs it takes (one CTA each, the data kernel leaves them
+// free).  The replay runs at full speed with one warp per SM sub-partition (128 threads) and about
+// a third slower with three (384 threads).  A bank that only runs the tuner + decimator is bound by
+// the replay itself, and in the pump the replay should finish beside the FFT: both get more SMs.
+// With the matched filter and bit timing behind it, the data kernels take longer than the replay
+// and keep the SMs.
+static int scout_threads(const jsdr_bpsk *b)
 {
-    static int t = 0;
-    if (!t) {
+    static int forced = -1;
+    if (forced < 0) {
         const char *e = getenv("JSDR_SCOUT_THREADS");          // (tuning aid)
-        t = e ? atoi(e) : 384;
-        if (t < 32 || t > kScoutThreads || (t & 31)) t = 384;
+        forced = e ? atoi(e) : 0;
+        if (forced < 32 || forced > kScoutThreads || (forced & 31)) forced = 0;
     }
-    return t;
+    if (forced) return forced;
+    return (b->stages == 1 || b->in_pump) ? 128 : 384;
 }
 
 // One thread per channel; a few hundred channels per CTA, so that a bank's replay occupies a handful of
@@ -855,7 +862,8 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
 {
     jsdr_ctx *ctx = b->ctx;
     ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
-    k_tuner_scout<<<(b->nchan + scout_threads() - 1) / scout_threads(), scout_threads(), 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+    const int st = scout_threads(b);
+    k_tuner_scout<<<(b->nchan + st - 1) / st, st, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
                                                              b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
@@ -915,6 +923,7 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int warps = sp.ncw * sp.nseg;
     const int grid = std::min((warps + W - 1) / W, sp.grid);
+    JSDR_CUDA(cudaMemsetAsync(sp.work_counter, 0, sizeof(unsigned), ctx->stream));
     ProfScope prof(ctx, JSDR_K_MIXDECIM, ctx->stream);
     kern<<<grid, W * 32, smem, ctx->stream>>>(sp);
     return launched(ctx, "k_mixdecim_stream");
@@ -942,8 +951,11 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     // one CTA per SM, warps loop over segments; the SMs the phase scout needs (on the
     // high-priority side stream) are left free so that the two never share an SM.  Segments:
     // about three per resident warp, their count chosen so that the last wave is full.
-    const int scout_ctas = (mp.nchan + scout_threads() - 1) / scout_threads();
-    sp.grid = std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
+    const int scout_ctas = (mp.nchan + scout_threads(b) - 1) / scout_threads(b);
+    // stand-alone, the replay of the next block runs beside this kernel: leave it its SMs.  In the
+    // pump it runs beside the FFT that precedes this kernel and is normally done by now, so every SM
+    // is taken; work is handed out dynamically, so an SM the scout still holds just joins late.
+    sp.grid = b->in_pump ? b->ctx->sm_count : std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
     sp.warps_per_cta = (FMT == FMT_S16) ? stream::kWarps : stream::kWarpsF32;
     const int resident = sp.grid * sp.warps_per_cta;
     int nseg = std::max(1, 3 * resident / sp.ncw);
@@ -953,6 +965,7 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     sp.nseg = (mp.NO + R - 1) / R;
     sp.ds_out = mp.ds_out;
     sp.max_ds = mp.max_ds;
+    sp.work_counter = reinterpret_cast<unsigned *>(b->d_nbits + b->nchan);   // one spare word behind nbits[]
     for (int k = 0; k < stream::kMaxTaps; k++) {
         sp.taps[k] = (k < b->ntaps) ? b->h_taps[k] : 0.0;
         sp.tapsf[k] = (float)sp.taps[k];
@@ -1257,7 +1270,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_ds_out, sizeof(double2) * nc * b->max_ds);
     ALLOC(b->d_vco_state, sizeof(double) * 2);
     ALLOC(b->d_ts, sizeof(TimingState) * nc);
-    ALLOC(b->d_nbits, sizeof(int32_t) * nc);
+    ALLOC(b->d_nbits, sizeof(int32_t) * (nc + 1));   // + the streaming kernel's work counter
 #undef ALLOC
     // tables and constants, computed on the host exactly as the reference's setup code does
     std::vector<double> cossin(512);
@@ -1520,7 +1533,10 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     if (mem == JSDR_MEM_DEVICE) {
         job.d_psd = psd;
         job.d_peak = peak_bin;
-        return bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
+        b->in_pump = 1;
+        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
+        b->in_pump = 0;
+        return rc;
     }
     if (f->out_cap < psd_elems * sizeof(float)) {
         cudaFree(f->d_out);
@@ -1563,7 +1579,10 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
             JSDR_CUDA(cudaMemcpyAsync(peak_bin + blk0, f->d_peak + blk0, sizeof(int32_t) * nblk,
                                       cudaMemcpyDeviceToHost, ctx->copy_out));
     }
-    JSDR_TRY(bpsk_receive<FMT_S16>(b, b->d_in, (int)S, S, 0, 0, JSDR_MEM_DEVICE));
+    b->in_pump = 1;
+    const int rc_bank = bpsk_receive<FMT_S16>(b, b->d_in, (int)S, S, 0, 0, JSDR_MEM_DEVICE);
+    b->in_pump = 0;
+    JSDR_TRY(rc_bank);
     JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;

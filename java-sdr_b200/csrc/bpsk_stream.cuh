@@ -50,6 +50,7 @@ struct Params {
     int n0, NO, R, nseg, ncw;           // first output's sample, outputs, outputs per segment, segments, channel groups
     int grid;                           // CTAs to launch (host side only)
     int warps_per_cta;                  // kWarps or kWarpsF32 (host side only)
+    unsigned *work_counter;             // zeroed before the launch
     double2 *ds_out;
     int max_ds;
     double taps[kMaxTaps];
@@ -297,7 +298,13 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
     const bool aligned = ((reinterpret_cast<size_t>(p.in) & 15) == 0) && ((p.chan_stride * (long long)sizeof(raw_t)) % 16 == 0);
     const bool iqcorr = FMT == FMT_S16 && (p.ic | p.qc) != 0;
 
-    for (int wg = blockIdx.x * W + warp; wg < p.ncw * p.nseg; wg += gridDim.x * W) {
+    // warps take (channel group, segment) items from a shared counter: an SM that became free
+    // late (the phase scout ran on it) simply takes fewer
+    for (;;) {
+        int wg = 0;
+        if (lane == 0) wg = (int)atomicAdd(p.work_counter, 1u);
+        wg = __shfl_sync(0xffffffffu, wg, 0);
+        if (wg >= p.ncw * p.nseg) break;
         const int cw = wg % p.ncw, seg = wg / p.ncw;
         const int ch0 = cw * 32;
         const int rows = min(32, p.nchan - ch0);

@@ -67,6 +67,7 @@ struct jsdr_bpsk {
     unsigned long long *d_tu_dx56 = nullptr; // [nchan] the same in 8.56 fixed point (streaming kernel)
     int precision = 0;               // JSDR_PREC_F64 (exact) or JSDR_PREC_F32 (decimator in binary32)
     int kernel_mode = 0;             // JSDR_KERNEL_AUTO / _TILE / _STREAM
+    int in_pump = 0;                 // set by jsdr_pump_receive_s16 around the bank's receive
     double *d_tu_phase0 = nullptr;   // [nchan] initial tuPhase (zeros)
     const double *d_tu_phase = nullptr;   // committed tuPhase: phase0 or the phase_end of the last plan used
     // Scout output ("plan") for one block.  Two of them: while the data kernels work
