@@ -93,7 +93,7 @@ def synth_tile(nchan, S, seed):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -111,8 +111,14 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+            r = [c.strip() for c in line.split(",")]
+            try:        # nvidia-smi's own timestamp (its stdout reaches us in bursts)
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = time.time()
+            self.rows.append((ts, r))
 
     def window(self, t0, t1):
         """Keep the samples taken inside the timed region (host clock, 30 ms slack)."""
@@ -127,11 +133,17 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        try:
+            self.th.join(timeout=1.0)
+        except Exception:
+            pass
         sm, mx, reasons = [], [], set()
         t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
-        for ts, r in self.rows:
-            if t0 is not None and not (t0 <= ts <= t1):
-                continue
+        rows = [(ts, r) for ts, r in self.rows if t0 is None or t0 <= ts <= t1]
+        scope = "timed region"
+        if not rows:    # too short a region for the sampling period: everything since before the warm-up
+            rows, scope = self.rows, "warm-up + timed region"
+        for ts, r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -140,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def cpu_pipeline(a, seconds, nthreads):
