@@ -235,6 +235,10 @@ extern "C" int jsdr_timer_stop_ms(jsdr_ctx *ctx, float *ms)
 {
     JSDR_REQUIRE(ctx && ms, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
+    // the timed region ends when the auxiliary stream (bit timing, frames) is done as well; the side
+    // stream only ever runs ahead (the next block's phase replay), so it is not waited for
+    JSDR_CUDA(cudaEventRecord(ctx->ev_aux_join, ctx->aux));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux_join, 0));
     JSDR_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
     JSDR_CUDA(cudaEventSynchronize(ctx->ev_t1));
     JSDR_CUDA(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));

@@ -155,12 +155,12 @@ __device__ __forceinline__ double phase_step2(double p, double inc, double th1, 
 
 constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
 
-// CTA size of the phase scout = how many SMs it takes (one CTA each, the data kernel leaves them
-// free).  The replay runs at full speed with one warp per SM sub-partition (128 threads) and about
-// a third slower with three (384 threads).  A bank that only runs the tuner + decimator is bound by
-// the replay itself, and in the pump the replay should finish beside the FFT: both get more SMs.
-// With the matched filter and bit timing behind it, the data kernels take longer than the replay
-// and keep the SMs.
+// CTA size of the phase scout = how many SMs it takes (one CTA each; the streaming data kernel
+// leaves them free when it runs beside it).  The replay runs at full speed with one warp per SM
+// sub-partition (128 threads: 18 cycles per sample) and about a third slower with three (384
+// threads); every user of the bank — the tuner + decimator alone, the pump (where it should finish
+// beside the FFT) and the full chain now that bit timing overlaps the next block — is bound by the
+// replay before it is bound by the SMs it takes, so it gets one warp per sub-partition.
 static int scout_threads(const jsdr_bpsk *b)
 {
     static int forced = -1;
@@ -170,7 +170,8 @@ static int scout_threads(const jsdr_bpsk *b)
         if (forced < 32 || forced > kScoutThreads || (forced & 31)) forced = 0;
     }
     if (forced) return forced;
-    return (b->stages == 1 || b->in_pump) ? 128 : 384;
+    (void)b;
+    return 128;
 }
 
 // One thread per channel; a few hundred channels per CTA, so that a bank's replay occupies a handful of
@@ -213,8 +214,8 @@ k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_
 
 // vcoPhase (:511-516) and dmBitPhase (:581-584) are the same for every channel of
 // a bank: warp 0 replays one, warp 1 the other.
-__global__ void k_vco_scout(double *__restrict__ state, uint8_t *__restrict__ vco_ix,
-                            uint8_t *__restrict__ bit_roll, int NO, double vco_inc,
+__global__ void k_vco_scout(const double *__restrict__ state, double *__restrict__ state_out,
+                            uint8_t *__restrict__ vco_ix, uint8_t *__restrict__ bit_roll, int NO, double vco_inc,
                             double bit_inc, double bit_time)
 {
     if (threadIdx.x == 0) {
@@ -224,7 +225,7 @@ __global__ void k_vco_scout(double *__restrict__ state, uint8_t *__restrict__ vc
             double q = __ddiv_rn(__dmul_rn(p, 256.0), kTwoPi);
             vco_ix[m] = (uint8_t)(__double2int_rz(q) & 255);
         }
-        state[0] = p;
+        state_out[0] = p;
     } else if (threadIdx.x == 32) {
         double b = state[1];
         for (int m = 0; m < NO; m++) {
@@ -236,7 +237,7 @@ __global__ void k_vco_scout(double *__restrict__ state, uint8_t *__restrict__ vc
             }
             bit_roll[m] = roll;
         }
-        state[1] = b;
+        state_out[1] = b;
     }
 }
 
@@ -701,21 +702,20 @@ struct TimingParams {
     long long cnt_ds0;
 };
 
-constexpr int kTimingTile = 32;      // 9600 S/s samples staged per channel per step
+constexpr int kTimingTile = 8;       // 9600 S/s samples per channel per step of the outer loop
 
 // :533-595, one lane per channel, one warp per CTA (the recurrence is latency bound, so the
-// warps are spread over as many SMs as there are).  The matched-filter output is staged through
-// shared memory in [32 channels][32 samples] tiles — one coalesced 512-byte row per warp
-// instruction, loaded one tile ahead — and each lane then walks its own row.
+// warps are spread over as many SMs as there are).  No shared memory and few registers, so that
+// these CTAs fit beside whatever else is resident (the kernel runs on the auxiliary stream, next to
+// the following block's tuner and matched filter): every lane reads its own row of the
+// matched-filter output, 16 bytes per sample, a tile of 8 samples ahead in registers.
 __global__ void __launch_bounds__(32) k_timing(const TimingParams p)
 {
     __shared__ double sE[8][32];                       // dmEnergy[], indexed by the running bit position
-    __shared__ double2 sDm[2][32][kTimingTile + 1];    // odd pitch in 16-byte units: row-per-lane reads do not conflict
     const int lane = threadIdx.x;
     const int ch0 = blockIdx.x * 32;
     const int ch = min(ch0 + lane, p.nchan - 1);
     const bool live = ch0 + lane < p.nchan;
-    const int rows = min(32, p.nchan - ch0);
     TimingState st = p.ts[ch];
 #pragma unroll
     for (int i = 0; i < 8; i++) sE[i][lane] = st.dmEnergy[i];
@@ -726,35 +726,35 @@ __global__ void __launch_bounds__(32) k_timing(const TimingParams p)
     int nb = 0;
     int8_t *bits = p.bits + (size_t)ch * p.max_bits;
     long long *bit_at = p.bit_at + (size_t)ch * p.max_bits;
+    const double2 *row = p.dm + (size_t)ch * p.max_ds;
 
     const int ntiles = (p.NO + kTimingTile - 1) / kTimingTile;
-    double2 pre[32];                                   // next tile: row r, this lane's sample
-    auto load_tile = [&](int t) {
-        const int m = t * kTimingTile + lane;
+    double2 cur[kTimingTile], nxt[kTimingTile];
+    auto load_tile = [&](int t, double2 (&dst)[kTimingTile]) {
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-            pre[r] = make_double2(0.0, 0.0);
-            if (r < rows && m < p.NO) pre[r] = p.dm[(size_t)(ch0 + r) * p.max_ds + m];
+        for (int j = 0; j < kTimingTile; j++) {
+            const int m = t * kTimingTile + j;
+            dst[j] = (m < p.NO) ? row[m] : make_double2(0.0, 0.0);
         }
     };
-    auto store_tile = [&](int t) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) sDm[t & 1][r][lane] = pre[r];
-    };
-    if (ntiles > 0) load_tile(0);
+    if (ntiles > 0) load_tile(0, nxt);
     for (int t = 0; t < ntiles; t++) {
-        __syncwarp();
-        store_tile(t);
-        if (t + 1 < ntiles) load_tile(t + 1);
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kTimingTile; j++) cur[j] = nxt[j];
+        if (t + 1 < ntiles) load_tile(t + 1, nxt);
         const int cnt = min(kTimingTile, p.NO - t * kTimingTile);
         // bit-phase roll-overs of this tile (the same for every channel): one bit per sample
-        const int mr = t * kTimingTile + lane;
-        const unsigned rollmask = __ballot_sync(0xffffffffu, mr < p.NO && p.bit_roll[mr] != 0);
+        unsigned rollmask = 0;
+#pragma unroll
+        for (int j = 0; j < kTimingTile; j++) {
+            const int m = t * kTimingTile + j;
+            if (m < p.NO && p.bit_roll[m] != 0) rollmask |= 1u << j;
+        }
         // Decisions of different channels fall on different samples (bitPos == peakPos), and two
         // decisions of one channel are at least 5 samples apart.  The per-sample part therefore
         // only notes the decision sample; the expensive part (:538-574) runs for all lanes
         // together once every 4 samples instead of diverging on every sample.
+#pragma unroll
         for (int j0 = 0; j0 < cnt; j0 += 4) {
             bool pend = false;
             double2 pf = make_double2(0.0, 0.0);
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(32) k_timing(const TimingParams p)
             for (int jj = 0; jj < 4; jj++) {
                 const int j = j0 + jj;
                 if (j < cnt) {
-                    const double2 f = sDm[t & 1][lane][j];
+                    const double2 f = cur[j];
                     const double energy1 = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));            // :534
                     sE[bitPos][lane] = __dadd_rn(__dmul_rn(sE[bitPos][lane], C1), __dmul_rn(energy1, S1));   // :535
                     if (bitPos == peakPos) {                                                               // :537
@@ -872,21 +872,42 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
     return JSDR_OK;
 }
 
+// Replay vcoPhase (:511-516) and dmBitPhase (:581-584) for NO samples from the committed state
+// into buffer kb (side stream).  The committed state is not touched: the output state becomes the
+// committed one when the block is actually consumed.
+int launch_vco_scout(jsdr_bpsk *b, int NO, int kb)
+{
+    jsdr_ctx *ctx = b->ctx;
+    const double vco_inc = 2.0 * M_PI * 1200.0 / (double)9600;      // :88
+    const double bit_inc = 1.0 / (double)9600, bit_time = 1.0 / (double)1200;   // :91-92
+    // (the bit-timing kernel of two blocks ago may still be reading this buffer)
+    if (b->bits_used[kb]) JSDR_CUDA(cudaStreamWaitEvent(ctx->side, b->ev_bits_done[kb], 0));
+    const int c = b->vco_state_cur;
+    k_vco_scout<<<1, 64, 0, ctx->side>>>(b->d_vco_state + 2 * c, b->d_vco_state + 2 * (c ^ 1), b->d_vco_ix[kb],
+                                         b->d_bit_roll[kb], NO, vco_inc, bit_inc, bit_time);
+    JSDR_TRY(launched(ctx, "k_vco_scout"));
+    JSDR_CUDA(cudaEventRecord(b->ev_vco_ready, ctx->side));
+    return JSDR_OK;
+}
+
 // Buffers of the 9600 S/s stages, allocated when a receive first needs them (a
 // stages==1 bank, e.g. the mix+FIR benchmark, never pays for them).
 int ensure_stage_buffers(jsdr_bpsk *b)
 {
-    if (b->d_dm_out) return JSDR_OK;
+    if (b->d_dm_buf[1]) return JSDR_OK;
     jsdr_ctx *ctx = b->ctx;
     const size_t nc = (size_t)b->nchan;
     struct { void **p; size_t bytes; } req[] = {
-        {(void **)&b->d_vco_ix, (size_t)b->max_ds},
-        {(void **)&b->d_bit_roll, (size_t)b->max_ds},
+        {(void **)&b->d_vco_ix[0], (size_t)b->max_ds},
+        {(void **)&b->d_vco_ix[1], (size_t)b->max_ds},
+        {(void **)&b->d_bit_roll[0], (size_t)b->max_ds},
+        {(void **)&b->d_bit_roll[1], (size_t)b->max_ds},
         {(void **)&b->d_dm_hist[0], sizeof(double2) * 64 * nc},
         {(void **)&b->d_dm_hist[1], sizeof(double2) * 64 * nc},
         {(void **)&b->d_bits, nc * b->max_bits},
         {(void **)&b->d_bit_at, sizeof(long long) * nc * b->max_bits},
-        {(void **)&b->d_dm_out, sizeof(double2) * nc * b->max_ds},
+        {(void **)&b->d_dm_buf[0], sizeof(double2) * nc * b->max_ds},
+        {(void **)&b->d_dm_buf[1], sizeof(double2) * nc * b->max_ds},
     };
     for (auto &r : req) {
         cudaError_t e = cudaMalloc(r.p, r.bytes);
@@ -897,6 +918,13 @@ int ensure_stage_buffers(jsdr_bpsk *b)
         }
         JSDR_CUDA(cudaMemsetAsync(*r.p, 0, r.bytes, ctx->stream));
     }
+    b->d_dm_out = b->d_dm_buf[0];
+    JSDR_CUDA(cudaEventCreateWithFlags(&b->ev_dm_ready, cudaEventDisableTiming));
+    JSDR_CUDA(cudaEventCreateWithFlags(&b->ev_vco_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) JSDR_CUDA(cudaEventCreateWithFlags(&b->ev_bits_done[i], cudaEventDisableTiming));
+    // the bit stage starts on the auxiliary stream: order it behind the clears above
+    JSDR_CUDA(cudaEventRecord(b->ev_dm_ready, ctx->stream));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->aux, b->ev_dm_ready, 0));
     return JSDR_OK;
 }
 
@@ -1039,7 +1067,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     JSDR_TRY(ctx->bind());
     b->last_nds = 0;
     if (S == 0) {
-        JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * b->nchan, ctx->stream));
+        JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * b->nchan, ctx->aux));
         if (b->fec && b->stages >= 3 && b->d_bits) JSDR_TRY(jsdr_fec_after_bits(b));   // no bits: no frames either
         return JSDR_OK;
     }
@@ -1057,11 +1085,11 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     if (!autotune && !(P.valid && P.S == S)) JSDR_TRY(launch_scout(b, P, S));
+    const int kb = b->bit_cur;                         // buffer of the 9600 S/s stages for this block
     if (b->stages >= 2 && NO > 0) {
-        const double vco_inc = 2.0 * M_PI * 1200.0 / (double)9600;      // :88
-        const double bit_inc = 1.0 / (double)9600, bit_time = 1.0 / (double)1200;   // :91-92
-        k_vco_scout<<<1, 64, 0, ctx->side>>>(b->d_vco_state, b->d_vco_ix, b->d_bit_roll, NO, vco_inc, bit_inc, bit_time);
-        JSDR_TRY(launched(ctx, "k_vco_scout"));
+        // normally replayed already, behind the previous block's tuner scout (look-ahead below)
+        if (!(b->vco_ahead_valid && b->vco_ahead_NO == NO && b->vco_ahead_kb == kb)) JSDR_TRY(launch_vco_scout(b, NO, kb));
+        b->vco_ahead_valid = false;
     }
     JSDR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
 
@@ -1082,7 +1110,8 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     }
     if (after_input) JSDR_TRY(after_input(user, d_in));
     if (!autotune) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ready, 0));
-    JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    // (ev_join — the VCO / bit-phase replay of this block — is only needed by the matched filter:
+    // the tuner + decimator runs beside it)
     if (autotune) {
         JSDR_TRY(autotune_block<FMT>(b, d_in, S, chan_stride, ic, qc, n0, NO));
     } else {
@@ -1169,17 +1198,21 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
 
     // ---- matched filter, bit timing
     if (b->stages >= 2 && NO > 0) {
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_vco_ready, 0));
+        b->vco_state_cur ^= 1;                         // this block's replay is consumed: its end state is committed
         DmParams dp;
         dp.ds = b->d_ds_out;
         dp.max_ds = b->max_ds;
         dp.NO = NO;
-        dp.vco_ix = b->d_vco_ix;
+        dp.vco_ix = b->d_vco_ix[kb];
         dp.hist_in = b->d_dm_hist[b->dm_hist_cur];
         dp.hist_out = b->d_dm_hist[b->dm_hist_cur ^ 1];
         dp.dmtaps = b->d_dmtaps;
         dp.cossin = b->d_cossin;
         dp.base65 = (int)(b->cnt_ds % 65);
-        dp.dm_out = b->d_dm_out;
+        dp.dm_out = b->d_dm_buf[kb];
+        b->d_dm_out = b->d_dm_buf[kb];
+        if (b->bits_used[kb]) JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_bits_done[kb], 0));
         dim3 grid((NO + kDm2Tile - 1) / kDm2Tile, nchan);
         const size_t dm_smem = sizeof(double2) * (size_t)(kDm2Tile + 64 + 16);
         static PerDeviceFlag dm_attr;
@@ -1194,28 +1227,50 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         JSDR_TRY(launched(ctx, "k_dm_tail"));
         b->dm_hist_cur ^= 1;
         if (b->stages >= 3) {
+            // bit timing on the auxiliary stream: it overlaps the next block's tuner + matched filter
+            JSDR_CUDA(cudaEventRecord(b->ev_dm_ready, ctx->stream));
+            JSDR_CUDA(cudaStreamWaitEvent(ctx->aux, b->ev_dm_ready, 0));
             TimingParams tp;
-            tp.dm = b->d_dm_out;
+            tp.dm = b->d_dm_buf[kb];
             tp.max_ds = b->max_ds;
             tp.NO = NO;
             tp.nchan = nchan;
-            tp.bit_roll = b->d_bit_roll;
+            tp.bit_roll = b->d_bit_roll[kb];
             tp.ts = b->d_ts;
             tp.bits = b->d_bits;
             tp.bit_at = b->d_bit_at;
             tp.nbits = b->d_nbits;
             tp.max_bits = b->max_bits;
             tp.cnt_ds0 = b->cnt_ds;
-            ProfScope prof(ctx, JSDR_K_TIMING, ctx->stream);
-            k_timing<<<(nchan + 31) / 32, 32, 0, ctx->stream>>>(tp);
+            {
+                ProfScope prof(ctx, JSDR_K_TIMING, ctx->aux);
+                k_timing<<<(nchan + 31) / 32, 32, 0, ctx->aux>>>(tp);
+            }
             JSDR_TRY(launched(ctx, "k_timing"));
+        }
+        b->bit_cur ^= 1;
+        // look ahead: the VCO / bit-phase replay of the next block (same length assumed), on the
+        // side stream behind the next block's tuner scout
+        const int no_next = (b->ds_cnt + S) / D;       // ds_cnt already carries this block
+        if (no_next > 0) {
+            JSDR_TRY(launch_vco_scout(b, no_next, b->bit_cur));
+            b->vco_ahead_valid = true;
+            b->vco_ahead_NO = no_next;
+            b->vco_ahead_kb = b->bit_cur;
         }
     }
     if (NO == 0)   // nothing reached the 9600 S/s stage in this call: no bits either
-        JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * nchan, ctx->stream));
-    if (b->fec && b->stages >= 3 && b->d_bits) JSDR_TRY(jsdr_fec_after_bits(b));   // :553-574
+        JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * nchan, ctx->aux));
+    if (b->fec && b->stages >= 3 && b->d_bits) JSDR_TRY(jsdr_fec_after_bits(b));   // :553-574, auxiliary stream
+    if (b->stages >= 3 && NO > 0) {
+        JSDR_CUDA(cudaEventRecord(b->ev_bits_done[kb], ctx->aux));
+        b->bits_used[kb] = true;
+    }
     b->cnt_ds += NO;
-    if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mem == JSDR_MEM_HOST) {
+        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
+    }
     return JSDR_OK;
 }
 
@@ -1268,7 +1323,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_ds_hist[0], sizeof(double2) * kMaxDsTaps * nc);
     ALLOC(b->d_ds_hist[1], sizeof(double2) * kMaxDsTaps * nc);
     ALLOC(b->d_ds_out, sizeof(double2) * nc * b->max_ds);
-    ALLOC(b->d_vco_state, sizeof(double) * 2);
+    ALLOC(b->d_vco_state, sizeof(double) * 4);
     ALLOC(b->d_ts, sizeof(TimingState) * nc);
     ALLOC(b->d_nbits, sizeof(int32_t) * (nc + 1));   // + the streaming kernel's work counter
 #undef ALLOC
@@ -1320,9 +1375,14 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     b->ctx->bind();
     cudaStreamSynchronize(b->ctx->side);
     cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(b->ctx->aux);
+    if (b->ev_dm_ready) cudaEventDestroy(b->ev_dm_ready);
+    if (b->ev_vco_ready) cudaEventDestroy(b->ev_vco_ready);
+    for (int i = 0; i < 2; i++)
+        if (b->ev_bits_done[i]) cudaEventDestroy(b->ev_bits_done[i]);
     void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
-                    b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix,
-                    b->d_bit_roll, b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_out, b->d_ts, b->d_bits,
+                    b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix[0], b->d_vco_ix[1],
+                    b->d_bit_roll[0], b->d_bit_roll[1], b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_buf[0], b->d_dm_buf[1], b->d_ts, b->d_bits,
                     b->d_bit_at, b->d_nbits, b->d_in, b->d_at_work[0], b->d_at_work[1], b->d_at_rev[0], b->d_at_rev[1], b->d_at_state};
     for (void *p : ptrs) cudaFree(p);
     jsdr_fec_destroy(b);
@@ -1456,16 +1516,16 @@ extern "C" int jsdr_bpsk_read_bits(jsdr_bpsk *b, int8_t *bits, int64_t *bit_at, 
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
     const cudaMemcpyKind kind = mem == JSDR_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    JSDR_CUDA(cudaMemcpyAsync(nbits, b->d_nbits, sizeof(int32_t) * b->nchan, kind, ctx->stream));
+    JSDR_CUDA(cudaMemcpyAsync(nbits, b->d_nbits, sizeof(int32_t) * b->nchan, kind, ctx->aux));
     const int w = max_bits < b->max_bits ? max_bits : b->max_bits;
     if (bits && w > 0)
         JSDR_CUDA(cudaMemcpy2DAsync(bits, (size_t)max_bits, b->d_bits, (size_t)b->max_bits, (size_t)w,
-                                    b->nchan, kind, ctx->stream));
+                                    b->nchan, kind, ctx->aux));
     if (bit_at && w > 0)
         JSDR_CUDA(cudaMemcpy2DAsync(bit_at, sizeof(int64_t) * max_bits, b->d_bit_at,
                                     sizeof(long long) * b->max_bits, sizeof(int64_t) * w, b->nchan, kind,
-                                    ctx->stream));
-    if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+                                    ctx->aux));
+    if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
 }
 
@@ -1476,8 +1536,8 @@ extern "C" int jsdr_bpsk_read_counters(jsdr_bpsk *b, int64_t *counters)
     JSDR_TRY(ctx->bind());
     std::vector<TimingState> ts(b->nchan);
     JSDR_CUDA(cudaMemcpyAsync(ts.data(), b->d_ts, sizeof(TimingState) * (size_t)b->nchan,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+                              cudaMemcpyDeviceToHost, ctx->aux));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     for (int c = 0; c < b->nchan; c++) {
         counters[4 * c + 0] = b->cnt_raw;
         counters[4 * c + 1] = b->cnt_ds;

@@ -446,23 +446,24 @@ extern "C" int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max
     JSDR_CUDA(cudaMemsetAsync(f->d_hist[0], 0, nc * fec::HIST, ctx->stream));     // dmFECCorr starts as zeros (:503)
     JSDR_CUDA(cudaMemsetAsync(f->d_nframes, 0, sizeof(int), ctx->stream));
     JSDR_CUDA(cudaMemsetAsync(f->d_cnt, 0, sizeof(long long) * 2 * nc, ctx->stream));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));            // the stage itself runs on the auxiliary stream
     b->fec = f;
     return JSDR_OK;
 }
 
-// called by bpsk_receive after the bit-timing stage
+// called by bpsk_receive after the bit-timing stage; like that stage it runs on the auxiliary stream
 int jsdr_fec_after_bits(jsdr_bpsk *b)
 {
     jsdr_fec_state *f = b->fec;
     jsdr_ctx *ctx = b->ctx;
     const int nchan = b->nchan, max_bits = b->max_bits;
-    JSDR_CUDA(cudaMemsetAsync(f->d_nframes, 0, sizeof(int), ctx->stream));
+    JSDR_CUDA(cudaMemsetAsync(f->d_nframes, 0, sizeof(int), ctx->aux));
     if (max_bits > 0) {
         dim3 grid((max_bits + 255) / 256, nchan);
         // cntBit lives at the end of each TimingState
         const long long *cnt_bit = reinterpret_cast<const long long *>(
             reinterpret_cast<const char *>(b->d_ts) + offsetof(jsdr::bpsk::TimingState, cntBit));
-        fec::k_sync<<<grid, 256, 0, ctx->stream>>>(f->d_hist[f->cur], b->d_bits, b->d_nbits, max_bits, nchan, cnt_bit,
+        fec::k_sync<<<grid, 256, 0, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, b->d_nbits, max_bits, nchan, cnt_bit,
                                                    (int)(sizeof(jsdr::bpsk::TimingState) / sizeof(long long)), f->d_frames,
                                                    f->d_nframes, f->max_frames, f->d_cnt);
         JSDR_TRY(launched(ctx, "k_sync"));
@@ -471,11 +472,11 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
     static PerDeviceFlag attr_done;
     if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(fec::k_fec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->stream>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
+    fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
                                                                f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan);
     JSDR_TRY(launched(ctx, "k_fec_decode"));
     dim3 g2((fec::HIST + 255) / 256, nchan);
-    fec::k_sync_shift<<<g2, 256, 0, ctx->stream>>>(f->d_hist[f->cur], f->d_hist[f->cur ^ 1], b->d_bits, b->d_nbits, max_bits);
+    fec::k_sync_shift<<<g2, 256, 0, ctx->aux>>>(f->d_hist[f->cur], f->d_hist[f->cur ^ 1], b->d_bits, b->d_nbits, max_bits);
     JSDR_TRY(launched(ctx, "k_sync_shift"));
     f->cur ^= 1;
     return JSDR_OK;
@@ -500,15 +501,15 @@ extern "C" int jsdr_bpsk_read_frames(jsdr_bpsk *b, int32_t *nframes, int32_t *ch
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
     int n = 0;
-    JSDR_CUDA(cudaMemcpyAsync(&n, f->d_nframes, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    JSDR_CUDA(cudaMemcpyAsync(&n, f->d_nframes, sizeof(int), cudaMemcpyDeviceToHost, ctx->aux));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     const int have = std::min(n, f->max_frames);
     std::vector<fec::FrameMeta> meta(have);
     std::vector<uint8_t> dat((size_t)have * 256);
     if (have > 0) {
-        JSDR_CUDA(cudaMemcpyAsync(meta.data(), f->d_frames, sizeof(fec::FrameMeta) * have, cudaMemcpyDeviceToHost, ctx->stream));
-        JSDR_CUDA(cudaMemcpyAsync(dat.data(), f->d_data, (size_t)have * 256, cudaMemcpyDeviceToHost, ctx->stream));
-        JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+        JSDR_CUDA(cudaMemcpyAsync(meta.data(), f->d_frames, sizeof(fec::FrameMeta) * have, cudaMemcpyDeviceToHost, ctx->aux));
+        JSDR_CUDA(cudaMemcpyAsync(dat.data(), f->d_data, (size_t)have * 256, cudaMemcpyDeviceToHost, ctx->aux));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     }
     // detection order on the device is not deterministic: report by (channel, bit)
     std::vector<int> order(have);
@@ -536,8 +537,8 @@ extern "C" int jsdr_bpsk_read_fec_counters(jsdr_bpsk *b, int64_t *cnt_fec, int64
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
     const size_t nc = (size_t)b->nchan;
-    JSDR_CUDA(cudaMemcpyAsync(cnt_fec, b->fec->d_cnt, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->stream));
-    JSDR_CUDA(cudaMemcpyAsync(cnt_dec, b->fec->d_cnt + nc, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->stream));
-    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    JSDR_CUDA(cudaMemcpyAsync(cnt_fec, b->fec->d_cnt, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->aux));
+    JSDR_CUDA(cudaMemcpyAsync(cnt_dec, b->fec->d_cnt + nc, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->aux));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
 }

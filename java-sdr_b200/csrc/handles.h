@@ -89,12 +89,24 @@ struct jsdr_bpsk {
     double2 *d_ds_out = nullptr;     // [nchan][max_ds]
     int last_nds = 0;
 
-    double *d_vco_state = nullptr;   // [2] vcoPhase, dmBitPhase (channel independent)
-    uint8_t *d_vco_ix = nullptr;     // [max_ds] table index per 9600 S/s sample
-    uint8_t *d_bit_roll = nullptr;   // [max_ds] 1 where dmBitPhase rolled over
+    double *d_vco_state = nullptr;   // [2][2] vcoPhase, dmBitPhase (channel independent): committed state and the replay's output
+    int vco_state_cur = 0;           // which half is the committed state
+    bool vco_ahead_valid = false;    // the replay of the NEXT block is already on the side stream
+    int vco_ahead_NO = 0, vco_ahead_kb = 0;
+    cudaEvent_t ev_vco_ready = nullptr;
+    // The bit-timing stage (and the frame stage behind it) runs on the context's auxiliary stream,
+    // beside the next block's tuner / matched filter on the main stream.  What it reads is therefore
+    // double buffered: matched-filter output, VCO table indices and bit-phase roll-overs of block k
+    // live in buffer k&1 until the timing kernel of block k has finished (ev_bits_done[k&1]).
+    uint8_t *d_vco_ix[2] = {nullptr, nullptr};     // [max_ds] table index per 9600 S/s sample
+    uint8_t *d_bit_roll[2] = {nullptr, nullptr};   // [max_ds] 1 where dmBitPhase rolled over
+    double2 *d_dm_buf[2] = {nullptr, nullptr};     // [nchan][max_ds] matched-filter output
+    cudaEvent_t ev_dm_ready = nullptr, ev_bits_done[2] = {nullptr, nullptr};
+    bool bits_used[2] = {false, false};
+    int bit_cur = 0;
     double2 *d_dm_hist[2] = {nullptr, nullptr};   // [nchan][64] last 64 VCO-mixed samples
     int dm_hist_cur = 0;
-    double2 *d_dm_out = nullptr;     // [nchan][max_ds]
+    double2 *d_dm_out = nullptr;     // the buffer of d_dm_buf[] the last receive filled
 
     jsdr::bpsk::TimingState *d_ts = nullptr;   // [nchan]
     int8_t *d_bits = nullptr;        // [nchan][max_bits]
