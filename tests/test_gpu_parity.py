@@ -438,3 +438,26 @@ def test_fft_persistent_plans_many_blocks_per_cta(ctx, n):
             assert np.max(np.abs(amp - np.sqrt(pw))) <= 2e-4, b
         assert pk[b] == int(np.argmax(psd[b, :n])) and psd[b, n + 1] == psd[b, pk[b]]
     f.close()
+
+
+def test_error_paths_return_codes_not_crashes(ctx):
+    """Nothing may throw through IAudioHandler.receive (JavaAudio.java:321-323): bad calls come
+    back as status codes with a message, and the handles stay usable."""
+    adsc = J.AudioDescriptor(96000)
+    with pytest.raises(J.JsdrError) as e:
+        J.fft(ctx, None, adsc, n=11 * 1024)                       # a prime factor outside 2, 3, 5, 7
+    assert e.value.code == -4                                     # JSDR_EUNSUPPORTED
+    f = J.fft(ctx, None, adsc, max_batch=2, n=1024)
+    with pytest.raises(J.JsdrError) as e:
+        f.receive_batch(np.zeros((3, 2048), np.float32))          # batch > max_batch
+    assert e.value.code == -1
+    assert f.receive(np.zeros(2048, np.float32))[1024 + 1] == np.float32(-3.4028234663852886e38)   # still works (Q4: all -inf)
+    f.close()
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0], max_block=4800)
+    with pytest.raises(J.JsdrError):
+        bank.receive(np.zeros(2 * 9600, np.float32))              # nsamples > max_block_samples
+    with pytest.raises(J.JsdrError):
+        bank.read_frames() if hasattr(bank, "_max_frames") else J._ck(J.lib().jsdr_bpsk_read_frames(bank.h, None, None, None, None, None, 0))
+    bank.receive(np.zeros(2 * 4800, np.float32))                  # and the bank is still usable
+    assert bank.read_ds().shape == (1, 480, 2)
+    bank.close()
