@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_generic_load(const void *__restrict__ i
 
 // fft.java:199-224 on a finished spectrum: one CTA per block
 __global__ void __launch_bounds__(256) k_generic_psd(const float2 *__restrict__ spec, float *__restrict__ out,
-                                                    int32_t *__restrict__ peak_bin, int N, int rate, float cf)
+                                                    int32_t *__restrict__ peak_bin, int N, int rate, float db_off)
 {
     __shared__ unsigned s_max;
     __shared__ int s_idx;
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) k_generic_psd(const float2 *__restrict__ 
     int best_idx = 0x7fffffff;
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const float2 v = x[k];
-        const float pw = __fmul_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), cf);
-        const float db = 3.0102999566398120f * lg2_approx(pw);
+        const float pw = fmaf(v.x, v.x, v.y * v.y);
+        const float db = fmaf(3.0102999566398120f, lg2_approx(pw), db_off);
         psd[k] = db;
         if (best < db) {           // k increases per thread: the first maximum wins
             best = db;
@@ -156,6 +156,7 @@ static int launch_fourstep(jsdr_fft *f, const Args &a, int in_fmt, int out_mode,
         fa.best = f->d_best + b0;
         fa.tw = a.tw;
         fa.cf = a.cf;
+        fa.db_off = a.db_off;
         fa.ic = a.ic;
         fa.qc = a.qc;
         int rc;
@@ -206,7 +207,7 @@ static int launch_generic(jsdr_fft *f, const Args &a, int in_fmt, int out_mode, 
         JSDR_CUDA(cudaMemcpyAsync(a.out, res, (size_t)total * sizeof(float2), cudaMemcpyDeviceToDevice, st));
         return JSDR_OK;
     }
-    k_generic_psd<<<a.nblocks, 256, 0, st>>>(res, a.out, a.peak_bin, f->n, a.rate, a.cf);
+    k_generic_psd<<<a.nblocks, 256, 0, st>>>(res, a.out, a.peak_bin, f->n, a.rate, a.db_off);
     return launched(ctx, "k_generic_psd");
 }
 
@@ -229,6 +230,7 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
         cf = (float)((double)cf / (32767.0 * 32767.0));
     }
     a.cf = cf;
+    a.db_off = (float)(10.0 * log10((double)cf));
     a.ic = ic;
     a.qc = qc;
     if (out_mode == OUT_SPECTRUM && in_fmt != IN_F32) {

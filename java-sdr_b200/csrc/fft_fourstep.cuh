@@ -25,7 +25,7 @@ struct FsArgs {
     unsigned long long *best;   // [nblocks] packed (ordered dB key << 32 | ~bin), reset to 0 before the chunk
     const float2 *tw;      // exp(-2*pi*i*t/N), t in [0, N)
     int nblocks;
-    float cf;
+    float cf, db_off;
     int ic, qc;
 };
 
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(256) k_fs_rows(const FsArgs a)
         int best_k = 0x7fffffff;
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-            const float pw = __fmul_rn(__fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y)), a.cf);
-            const float db = 3.0102999566398120f * lg2_approx(pw);
+            const float pw = fmaf(v[q].x, v[q].x, v[q].y * v[q].y);
+            const float db = fmaf(3.0102999566398120f, lg2_approx(pw), a.db_off);
             const int k = k1 + N1 * (j + 16 * q);
             stg_stream_f32(psd + k, db);
             if (best < db) {                       // k increases with q: the first maximum wins
