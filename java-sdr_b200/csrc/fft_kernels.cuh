@@ -296,6 +296,19 @@ struct Plan {
     // fetch the next block's pass-0 samples into registers before the last pass of the current
     // one (s16 input: one register per sample).
     static constexpr bool PERSIST = (G_ == 1) && (N_ >= 9600);
+    // CTAs per SM the kernel is compiled for: what shared memory allows, at the register budget
+    // the largest register DFT needs.  Radix <= 16 fits 48 registers (4096 = 16^3 then keeps five
+    // CTAs per SM instead of slipping to four); radix 32 fits 80, and a 256-thread CTA at 81..88
+    // registers drops from three per SM to two (measured on N = 512: 0.46 against 0.60 of peak).
+    // Odd radices and the persistent plans are left to the compiler (0 = unspecified).
+    static constexpr int RMAX = (R0_ > R1_ ? R0_ : R1_) > (R2_ > R3_ ? R2_ : R3_) ? (R0_ > R1_ ? R0_ : R1_) : (R2_ > R3_ ? R2_ : R3_);
+    static constexpr int REG_BUDGET = (RMAX <= 16) ? 48 : 80;
+    static constexpr int MINB_SMEM = (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int MINB_REGS = 65536 / (T_ * REG_BUDGET);
+    static constexpr int MINB_FIT = (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS) < 1 ? 1 : (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS);
+    static constexpr int MINB = (RMAX > 32 || (RMAX & (RMAX - 1)) != 0 || PERSIST) ? 0 : MINB_FIT;
+    static constexpr bool PACK_IN = true;
+    static constexpr bool GROUP_IN = true;
     static constexpr int NB0 = N_ / R0_;
     static constexpr int PRE_IT = (NB0 + T_ - 1) / T_;        // pass-0 butterflies per thread
 };
@@ -327,6 +340,19 @@ __device__ __forceinline__ float lg2_approx(float x)
     return r;
 }
 
+// exact s16 pair -> float pair without the conversion pipe: bias to unsigned, splice into the
+// mantissa of 2^23, subtract 2^23 + 32768 (both halves in one FADD2).  The 1/32767 of
+// JavaAudio.java:283 is folded into cf (the transform is linear).
+template <bool PACK>
+__device__ __forceinline__ float2 s16_bits_to_float(uint32_t w)
+{
+    w ^= 0x80008000u;
+    const float2 b = make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
+                                 __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)));
+    if constexpr (PACK) return cadd(b, make_float2(-8421376.0f, -8421376.0f));
+    else return make_float2(b.x - 8421376.0f, b.y - 8421376.0f);
+}
+
 template <class P, int IN>
 __device__ __forceinline__ float2 load_sample(const Args &a, long blk, int n)
 {
@@ -341,22 +367,8 @@ __device__ __forceinline__ float2 load_sample(const Args &a, long blk, int n)
         }
         // exact s16 -> float without the conversion pipe: bias to unsigned, splice into
         // the mantissa of 2^23, subtract 2^23 + 32768
-        w ^= 0x80008000u;
-        return cadd(make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
-                                __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432))),
-                    make_float2(-8421376.0f, -8421376.0f));       // both halves in one FADD2
+        return s16_bits_to_float<P::PACK_IN>(w);
     }
-}
-
-__device__ __forceinline__ float2 s16_pair_to_float(const Args &a, uint32_t w)
-{   // as in load_sample
-    if (a.ic | a.qc) {
-        w = (((w & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((w >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
-    }
-    w ^= 0x80008000u;
-    return cadd(make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
-                            __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432))),
-                make_float2(-8421376.0f, -8421376.0f));
 }
 
 template <int R, int M>
@@ -388,7 +400,7 @@ __device__ __forceinline__ void middle_pass(float2 *sm, const float2 *__restrict
 }
 
 template <class P, int IN, int OUT>
-__global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
+__global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
@@ -439,9 +451,26 @@ __global__ void __launch_bounds__(P::T) fft_kernel(const Args a)
             long blk = blk0 + g;
             if (blk >= a.nblocks) continue;
             float2 v[R0];
-            if constexpr (PREFETCH) {
+            if constexpr (IN == IN_S16 && P::GROUP_IN) {
+                uint32_t w[R0];
+                if constexpr (PREFETCH) {
 #pragma unroll
-                for (int m = 0; m < R0; m++) v[m] = s16_pair_to_float(a, pre[it][m]);
+                    for (int m = 0; m < R0; m++) w[m] = pre[it][m];
+                } else {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in) + blk * N + c;
+#pragma unroll
+                    for (int m = 0; m < R0; m++) w[m] = ldg_stream_u32(src + m * NB0);
+                }
+                // JavaAudio.java:281-288: s += (short)ic with 16-bit wrap.  A real (uniform) branch
+                // around the whole group: the correction is normally zero and predicated-off
+                // instructions would still take issue slots.
+                if (a.ic | a.qc) {
+#pragma unroll
+                    for (int m = 0; m < R0; m++)
+                        w[m] = (((w[m] & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((w[m] >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
+                }
+#pragma unroll
+                for (int m = 0; m < R0; m++) v[m] = s16_bits_to_float<P::PACK_IN>(w[m]);
             } else {
 #pragma unroll
                 for (int m = 0; m < R0; m++) v[m] = load_sample<P, IN>(a, blk, c + m * NB0);
