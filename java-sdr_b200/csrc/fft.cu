@@ -233,6 +233,7 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
     a.db_off = (float)(10.0 * log10((double)cf));
     a.ic = ic;
     a.qc = qc;
+    a.pf_dist = 0;
     if (out_mode == OUT_SPECTRUM && in_fmt != IN_F32) {
         set_error("spectrum output needs float input");
         return JSDR_EINVAL;

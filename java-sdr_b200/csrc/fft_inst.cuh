@@ -17,16 +17,16 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
-    if constexpr (P::PERSIST) {   // resident CTAs loop over the blocks
-        static int per_sm = 0;                    // a property of the kernel and sm_100a, not of the device index
-        if (!per_sm) {
-            JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, P::SMEM));
-            per_sm = std::max(1, per_sm);
-        }
-        grid = std::min(grid, per_sm * ctx->sm_count);
+    static int per_sm = 0;                        // a property of the kernel and sm_100a, not of the device index
+    if (!per_sm) {
+        JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, P::SMEM));
+        per_sm = std::max(1, per_sm);
     }
+    Args b = a;
+    if constexpr (P::PERSIST) grid = std::min(grid, per_sm * ctx->sm_count);   // resident CTAs loop over the blocks
+    else b.pf_dist = ctx->l2_prefetch ? per_sm * ctx->sm_count : 0;            // L2 look-ahead distance in CTAs
     ProfScope prof(ctx, JSDR_K_FFT, st);
-    kern<<<grid, P::T, P::SMEM, st>>>(a);
+    kern<<<grid, P::T, P::SMEM, st>>>(b);
     return launched(ctx, "fft_kernel");
 }
 

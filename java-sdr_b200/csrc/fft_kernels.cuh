@@ -121,8 +121,9 @@ __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.
 __device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
-{   // a*b = a.x*(b.x,b.y) + a.y*(-b.y,b.x)
-    return pfma(bcast(a.y), mul_pi(b), pmul(bcast(a.x), b));
+{   // a*b = a.x*b + i*(a.y*b): the half-swap and the sign ride on the FFMA2 addend, so this
+    // is two instructions and no rotated copy of either operand is ever materialised
+    return pfma(bcast(a.x), b, mul_pi(pmul(bcast(a.y), b)));
 }
 
 // a * exp(-2*pi*i*K/R), K and R compile-time
@@ -149,7 +150,7 @@ __device__ __forceinline__ float2 cmul_w(float2 a)
     } else {
         constexpr float c = (float)cx_cos2pi(k, R);
         constexpr float sn = (float)(-cx_sin2pi(k, R));   // w = (c, sn)
-        return pfma(bcast(a.y), make_float2(-sn, c), pmul(bcast(a.x), make_float2(c, sn)));
+        return pfma(a, bcast(c), mul_pi(pmul(a, bcast(sn))));   // scalar immediates, no constant pairs
     }
 }
 
@@ -267,6 +268,24 @@ struct Dft<R, false> {
 template <int R>
 __device__ __forceinline__ void twiddle_powers(float2 *v, float2 w1)
 {
+    if constexpr (R >= 64 && R % 8 == 0) {
+        // large radix: r = 8a + b, w1^r = (w1^8)^a * w1^b.  The same number of complex products
+        // as the tree below, but only 7 + R/8 powers are ever live instead of R/2.
+        constexpr int A = R / 8;
+        float2 wb[8], wa[A];
+        wb[1] = w1;
+#pragma unroll
+        for (int b = 2; b < 8; b++) wb[b] = cmul(wb[b / 2], wb[b - b / 2]);
+        wa[1] = cmul(wb[4], wb[4]);
+#pragma unroll
+        for (int q = 2; q < A; q++) wa[q] = cmul(wa[q / 2], wa[q - q / 2]);
+#pragma unroll
+        for (int r = 1; r < R; r++) {
+            if (r % 8) v[r] = cmul(v[r], wb[r % 8]);
+            if (r / 8) v[r] = cmul(v[r], wa[r / 8]);
+        }
+        return;
+    }
     float2 w[R];
     w[0] = make_float2(1.f, 0.f);
     if (R > 1) w[1] = w1;
@@ -323,6 +342,7 @@ struct Args {
     float cf;             // (2/N)^2, times 1/32767^2 for s16 input
     float db_off;         // 10*log10(cf): psd = 10*log10(re^2+im^2) + db_off, one FFMA behind the logarithm
     int ic, qc;           // I/Q DC correction added with 16-bit wrap (s16 input)
+    int pf_dist;          // CTAs resident on the device (0: no L2 prefetch), see fft_kernel
 };
 
 __device__ __forceinline__ unsigned ordered_key(float v)
@@ -433,6 +453,24 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
     // one pass for ordinary plans (a CTA owns blocks blk0 .. blk0+G-1); persistent plans loop
     long blk0 = (long)blockIdx.x * P::G;
     const long blk_step = gridDim.x;
+
+    // Ordinary plans: CTAs start in blockIdx order, so the CTA that takes this one's place is
+    // about pf_dist further on.  One bulk prefetch pulls its input into L2 now; its pass-0 loads
+    // then wait for L2 instead of HBM (the few resident CTAs of the large-radix plans cannot hide
+    // an HBM round trip behind each other).  Only the 16-byte-aligned interior of the range is
+    // touched, and only whole groups inside the batch.
+    if constexpr (!P::PERSIST) {
+        if (tid == 0 && a.pf_dist > 0) {
+            const long nb = blk0 + (long)a.pf_dist * P::G;
+            if (nb + P::G <= a.nblocks) {
+                constexpr size_t EL = (IN == IN_S16) ? 4 : 8;
+                const size_t lo = (reinterpret_cast<size_t>(a.in) + (size_t)nb * N * EL + 15) & ~(size_t)15;
+                const size_t hi = (reinterpret_cast<size_t>(a.in) + (size_t)(nb + P::G) * N * EL) & ~(size_t)15;
+                if (hi > lo)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+            }
+        }
+    }
     do {
 
     if (OUT == OUT_PSD && tid < P::G) {
@@ -487,10 +525,13 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                 int r2 = t % P::R2, r1 = t / P::R2;
                 pos = r3 * P::PITCH + r2 * (R0 * P::R1) + r1 * R0;
             }
-            float4 *dst = reinterpret_cast<float4 *>(sm + g * P::FFT_ELEMS + pos);
-#pragma unroll
-            for (int m = 0; m < R0 / 2; m++)
-                dst[m] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
+            // 64-bit stores: pairing the outputs for 128-bit ones costs more register moves
+            // than the stores it saves (the shared-memory wavefront count is the same)
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + g * P::FFT_ELEMS + pos);
+            static_for<0, R0>([&](auto mm) {
+                constexpr int m = decltype(mm)::value;
+                asm volatile("st.shared.v2.f32 [%0+%1], {%2,%3};" ::"r"(dst), "n"(m * 8), "f"(v[m].x), "f"(v[m].y) : "memory");
+            });
         }
         }
     }
@@ -515,7 +556,6 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
         // running first-strict-maximum exactly as fft.java:201-211: m starts at
         // -Float.MAX_VALUE, a bin wins only if m < psd (NaN and -inf never do)
         float best = -3.4028234663852886e38f;
-        int best_idx = 0x7fffffff;
         int my_g = 0;
         for (int U = tid; U < P::G * ML; U += P::T) {
             int g = U / ML, j = U - g * ML;
@@ -535,8 +575,6 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                 for (int q = 0; q < RL; q++) stg_stream_f2(spec + j + q * ML, v[q]);
             } else {
                 float *psd = a.out + blk * (long)(N + 2);
-                float it_best = -3.4028234663852886e38f;
-                int it_idx = 0x7fffffff;
 #pragma unroll
                 for (int q = 0; q < RL; q++) {
                     // fft.java:207 (re*re + im*im) * cf -> dB.  The scale is applied behind the logarithm
@@ -545,20 +583,15 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                     float pw = fmaf(v[q].x, v[q].x, v[q].y * v[q].y);
                     // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is accurate to ~1e-7 in log2
                     float db = fmaf(3.0102999566398120f, lg2_approx(pw), a.db_off);
-                    int k = j + q * ML;
-                    stg_stream_f32(psd + k, db);
-                    if (it_best < db) {            // bins visited in increasing k: first maximum wins
-                        it_best = db;
-                        it_idx = k;
-                    }
-                }
-                if (best < it_best || (best == it_best && it_idx < best_idx)) {
-                    best = it_best;
-                    best_idx = it_idx;
+                    stg_stream_f32(psd + j + q * ML, db);
+                    // only the running maximum here (one FMNMX; NaN never wins, and neither does
+                    // anything <= -Float.MAX_VALUE); the thread that turns out to hold the block's
+                    // maximum finds the bin afterwards
+                    best = fmaxf(best, db);
                 }
             }
         }
-        const unsigned best_key = (best_idx == 0x7fffffff) ? 0u : ordered_key(best);
+        const unsigned best_key = (best > -3.4028234663852886e38f) ? ordered_key(best) : 0u;
         if constexpr (OUT == OUT_PSD) {
             // first strict maximum (fft.java:208-211): max value, lowest bin among equals
             constexpr bool WARP_UNIFORM = (P::G == 1) || (ML % 32 == 0);
@@ -572,7 +605,24 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             }
             __syncthreads();
             unsigned gmax = s_max[my_g];
-            if (best_key != 0u && best_key == gmax) atomicMin(&s_idx[my_g], best_idx);
+            if (best_key != 0u && best_key == gmax) {
+                // rare: re-read this thread's own dB values (just written, L2) for the first bin
+                // that equals the maximum -- lowest bin among equals, as the strict '<' of :208 gives
+                int best_idx = 0x7fffffff;
+#pragma unroll 1
+                for (int U = tid; U < P::G * ML; U += P::T) {
+                    const int g = U / ML, j = U - g * ML;
+                    const long blk = blk0 + g;
+                    if (blk >= a.nblocks) continue;
+                    const float *psd = a.out + blk * (long)(N + 2);
+#pragma unroll 1
+                    for (int q = 0; q < RL; q++) {
+                        const int k = j + q * ML;
+                        if (k < best_idx && __ldcg(psd + k) == best) best_idx = k;
+                    }
+                }
+                atomicMin(&s_idx[my_g], best_idx);
+            }
             __syncthreads();
             if (tid < P::G && blk0 + tid < a.nblocks) {
                 long blk = blk0 + tid;
