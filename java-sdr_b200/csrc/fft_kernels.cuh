@@ -557,11 +557,24 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
         // -Float.MAX_VALUE, a bin wins only if m < psd (NaN and -inf never do)
         float best = -3.4028234663852886e38f;
         int my_g = 0;
-        for (int U = tid; U < P::G * ML; U += P::T) {
+        // the dB values stay in registers (one per bin, replacing the two of the spectrum value)
+        // until the block's maximum is known: only the thread that holds it looks for the bin
+        constexpr int ITERS = (P::G * ML + P::T - 1) / P::T;
+        float db[OUT == OUT_PSD ? ITERS : 1][OUT == OUT_PSD ? RL : 1];
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            const int U = tid + it * P::T;
+            if (ITERS * P::T != P::G * ML && U >= P::G * ML) break;
             int g = U / ML, j = U - g * ML;
             long blk = blk0 + g;
             my_g = g;
-            if (blk >= a.nblocks) continue;
+            if (blk >= a.nblocks) {
+                if constexpr (OUT == OUT_PSD) {
+#pragma unroll
+                    for (int q = 0; q < RL; q++) db[it][q] = -3.4028234663852886e38f;
+                }
+                continue;
+            }
             float2 v[RL];
             const float2 *p = sm + g * P::FFT_ELEMS + j;
 #pragma unroll
@@ -582,12 +595,11 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                     // (4e-7 dB) from the reference's float sequence, far inside the 1e-4 tolerance.
                     float pw = fmaf(v[q].x, v[q].x, v[q].y * v[q].y);
                     // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is accurate to ~1e-7 in log2
-                    float db = fmaf(3.0102999566398120f, lg2_approx(pw), a.db_off);
-                    stg_stream_f32(psd + j + q * ML, db);
-                    // only the running maximum here (one FMNMX; NaN never wins, and neither does
-                    // anything <= -Float.MAX_VALUE); the thread that turns out to hold the block's
-                    // maximum finds the bin afterwards
-                    best = fmaxf(best, db);
+                    db[it][q] = fmaf(3.0102999566398120f, lg2_approx(pw), a.db_off);
+                    stg_stream_f32(psd + j + q * ML, db[it][q]);
+                    // only the running maximum here (FMNMX; NaN never wins, and neither does
+                    // anything <= -Float.MAX_VALUE)
+                    best = fmaxf(best, db[it][q]);
                 }
             }
         }
@@ -606,20 +618,16 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             __syncthreads();
             unsigned gmax = s_max[my_g];
             if (best_key != 0u && best_key == gmax) {
-                // rare: re-read this thread's own dB values (just written, L2) for the first bin
-                // that equals the maximum -- lowest bin among equals, as the strict '<' of :208 gives
+                // one thread per block as a rule: the lowest of its bins that equals the maximum
+                // (what the strict '<' of :208 keeps), from the registers
                 int best_idx = 0x7fffffff;
-#pragma unroll 1
-                for (int U = tid; U < P::G * ML; U += P::T) {
-                    const int g = U / ML, j = U - g * ML;
-                    const long blk = blk0 + g;
-                    if (blk >= a.nblocks) continue;
-                    const float *psd = a.out + blk * (long)(N + 2);
-#pragma unroll 1
-                    for (int q = 0; q < RL; q++) {
-                        const int k = j + q * ML;
-                        if (k < best_idx && __ldcg(psd + k) == best) best_idx = k;
-                    }
+#pragma unroll
+                for (int it = 0; it < ITERS; it++) {
+                    const int U = tid + it * P::T;
+                    const int j = U - (U / ML) * ML;
+#pragma unroll
+                    for (int q = 0; q < RL; q++)
+                        if (db[it][q] == best) best_idx = min(best_idx, j + q * ML);
                 }
                 atomicMin(&s_idx[my_g], best_idx);
             }

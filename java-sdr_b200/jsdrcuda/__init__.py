@@ -126,7 +126,8 @@ def lib() -> C.CDLL:
         if not os.path.exists(_SO):
             raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")
-        _lib = C.CDLL(_SO)
+        # JSDR_LIB: another build of the same library (kernel experiments, tools/kbench.py)
+        _lib = C.CDLL(os.environ.get("JSDR_LIB") or _SO)
         for name, args in _SIGS.items():
             fn = getattr(_lib, name)
             fn.argtypes = args

@@ -72,14 +72,22 @@ def mix(nchan=4096, S=131072, rate=192000, ntaps=64):
     ctx.close()
 
 
-def fft(ns, total=1 << 28):
+def fft(ns, total=None):
+    # KBENCH_TOTAL: samples per launch (default 2^28); KBENCH_FILL=0: random data only
+    # in the first 8 MB (the rest of a fresh allocation reads as zeros: no arg-max work, less power)
+    total = total or int(os.environ.get("KBENCH_TOTAL", 1 << 28))
+    fill = os.environ.get("KBENCH_FILL", "1") != "0"
     ctx = J.Context(0)
     rng = np.random.default_rng(2)
     for n in ns:
         batch = max(1, total // n)
         f = J.fft(ctx, None, J.AudioDescriptor(192000), max_batch=batch, n=n)
         d_in = ctx.dev_alloc(batch * n * 8)
-        d_in.upload(rng.integers(-20000, 20000, 1 << 22).astype(np.int16))
+        tile = rng.integers(-20000, 20000, 1 << 22).astype(np.int16)
+        d_in.upload(tile)
+        if fill:
+            for off in range(tile.nbytes, batch * n * 4, tile.nbytes):
+                d_in.upload(tile[: min(tile.size, (batch * n * 4 - off) // 2)], offset=off)
         d_psd = ctx.dev_alloc(batch * (n + 2) * 4)
         d_pk = ctx.dev_alloc(batch * 4)
         for s16 in (True, False):
