@@ -98,15 +98,15 @@ struct RawT<FMT_F32> { typedef float2 type; };
 template <>
 struct RawT<FMT_S16> { typedef uint32_t type; };
 
-// (float)s / 32767f, correctly rounded, without the generic division: q0 = s*r,
-// e = fma(-q0, 32767, s), q = fma(r, e, q0) with r = fl(1/32767).  Checked
-// exhaustively against IEEE division for all 65536 inputs (tests/test_oracle.py).
+// (float)s / 32767f, correctly rounded, without the generic division.  s/32767 = s*2^-15 repeated
+// with period 15 bits, so it never comes within 2^-39 (relative) of a float rounding boundary,
+// and 1/32767 split as r_hi + r_lo (two floats, 48 bits) gives the correctly rounded quotient
+// in one multiply and one FMA: q = fma(s, r_hi, s*r_lo).  Checked exhaustively against IEEE
+// division for all 65536 inputs (tests/test_oracle.py).
 __device__ __forceinline__ float s16_over_32767(float x)
 {
-    const float r = 3.0518509447574615e-05f;
-    const float q0 = __fmul_rn(x, r);
-    const float e = __fmaf_rn(-q0, 32767.0f, x);
-    return __fmaf_rn(r, e, q0);
+    const float r_hi = 3.0518509447574615e-05f, r_lo = 2.8422576792141996e-14f;
+    return __fmaf_rn(x, r_hi, __fmul_rn(x, r_lo));
 }
 
 template <int FMT>

@@ -200,12 +200,10 @@ __device__ __forceinline__ void period_body(const Params &p, const typename Raw<
         if constexpr (PREC == PREC_F64) {
             double xi, xq;
             if constexpr (FMT == FMT_S16) {
-                // (float)s / 32767f, correctly rounded (JavaAudio.java:283): q0 = s*r, e = fma(-q0, 32767, s),
-                // q = fma(r, e, q0) with r = fl(1/32767) — s16_over_32767 of bpsk.cu on both halves at once
-                const float2 r2 = make_float2(3.0518509447574615e-05f, 3.0518509447574615e-05f);
-                const float2 q0 = mul2(f2, r2);
-                const float2 e2 = fma2(q0, make_float2(-32767.0f, -32767.0f), f2);
-                const float2 q2 = fma2(r2, e2, q0);
+                // (float)s / 32767f, correctly rounded (JavaAudio.java:283): fma(s, r_hi, s*r_lo), the
+                // s16_over_32767 of bpsk.cu on both halves at once
+                const float2 q2 = fma2(f2, make_float2(3.0518509447574615e-05f, 3.0518509447574615e-05f),
+                                       mul2(f2, make_float2(2.8422576792141996e-14f, 2.8422576792141996e-14f)));
                 xi = (double)q2.x;
                 xq = (double)q2.y;
             } else {
@@ -350,26 +348,32 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if constexpr (FMT == FMT_S16) {
-                    dst[0] = pre[i].x;
-                    dst[1] = pre[i].y;
-                    dst[2] = pre[i].z;
-                    dst[3] = pre[i].w;
-                    if (pos < MIR) {                               // mirror of ring positions 0 .. MIR-1
-                        dst[kRing + 0] = pre[i].x;
-                        dst[kRing + 1] = pre[i].y;
-                        dst[kRing + 2] = pre[i].z;
-                        dst[kRing + 3] = pre[i].w;
-                    }
+                    dst[i * RW + 0] = pre[i].x;
+                    dst[i * RW + 1] = pre[i].y;
+                    dst[i * RW + 2] = pre[i].z;
+                    dst[i * RW + 3] = pre[i].w;
                 } else {
-                    uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+                    uint2 *d2 = reinterpret_cast<uint2 *>(dst + i * RW);
                     d2[0] = make_uint2(pre[i].x, pre[i].y);
                     d2[1] = make_uint2(pre[i].z, pre[i].w);
-                    if (pos < MIR) {
+                }
+            }
+            // mirror of ring positions 0 .. MIR-1: a branch of its own, so that the chunks that
+            // land in the other ring slots (every second one, or three in four) skip it entirely
+            if (pos < MIR) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if constexpr (FMT == FMT_S16) {
+                        dst[i * RW + kRing + 0] = pre[i].x;
+                        dst[i * RW + kRing + 1] = pre[i].y;
+                        dst[i * RW + kRing + 2] = pre[i].z;
+                        dst[i * RW + kRing + 3] = pre[i].w;
+                    } else {
+                        uint2 *d2 = reinterpret_cast<uint2 *>(dst + i * RW);
                         d2[kRing + 0] = make_uint2(pre[i].x, pre[i].y);
                         d2[kRing + 1] = make_uint2(pre[i].z, pre[i].w);
                     }
                 }
-                dst += RW;
             }
         };
 
@@ -414,15 +418,21 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
                     x_top = phase_to_x56(ck) + (unsigned long long)((long long)(s_hi - (c << 5) + 1)) * dx;
                     bad_anchor = !(ck >= 0.0);
                 }
-                unsigned long long x = x_top;
+                // Sample j of the period sits j steps below the top: hi32(x_top - j*dx) lies in
+                // [X - j, X] for X = hi32(x_top) - j*hi32(dx) (the low words can borrow at most j), so
+                // the index is X's top byte unless X's 24 fraction bits are within j + 1 of an
+                // integer -- one multiply-add per sample instead of a 64-bit running difference,
+                // and no chain from sample to sample.  `near` lanes replay exactly (about one
+                // period in 2^14 per lane).
+                const unsigned xt = (unsigned)(x_top >> 32), ndx = 0u - (unsigned)(dx >> 32);
+                const unsigned nt = (xt << 8) + 256u, ndx8 = ndx << 8;
                 x_top -= dxD;
                 bool near = exact_lane || bad_anchor;
 #pragma unroll
                 for (int j = 0; j < DD; j++) {
-                    const unsigned xh = (unsigned)(x >> 32);
-                    taddr[j] = lane_tab + ((xh >> 17) & 0x7f80u);   // entry (index) of this lane's copy
-                    near |= (xh * 256u + 256u) <= 256u;      // fraction within 2^-24 of an integer
-                    x -= dx;
+                    const unsigned xj = xt + (unsigned)j * ndx;
+                    taddr[j] = lane_tab + ((xj >> 17) & 0x7f80u);   // entry (index) of this lane's copy
+                    near |= (nt + (unsigned)j * ndx8) <= 256u * (unsigned)(DD + 2);   // fraction in [-1, DD] * 2^-24
                 }
                 if (__any_sync(0xffffffffu, near)) {
                     if (near) {

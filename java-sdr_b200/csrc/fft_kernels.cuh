@@ -360,17 +360,26 @@ __device__ __forceinline__ float lg2_approx(float x)
     return r;
 }
 
-// exact s16 pair -> float pair without the conversion pipe: bias to unsigned, splice into the
-// mantissa of 2^23, subtract 2^23 + 32768 (both halves in one FADD2).  The 1/32767 of
-// JavaAudio.java:283 is folded into cf (the transform is linear).
+// exact s16 pair -> float pair.  CVT: one I2F.S16 per half on the conversion (XU) pipe -- two
+// instructions and nothing on the FMA pipe, which is the one this kernel saturates.  Otherwise
+// (the default; -DJSDR_FFT_CVT=1 selects the I2F form, measured 2-3% slower: it shares the XU pipe with MUFU.LG2): bias to unsigned, splice into the mantissa
+// of 2^23, subtract 2^23 + 32768 with one FADD2.  The 1/32767 of JavaAudio.java:283 is folded
+// into cf (the transform is linear).
+#ifndef JSDR_FFT_CVT
+#define JSDR_FFT_CVT 0
+#endif
 template <bool PACK>
 __device__ __forceinline__ float2 s16_bits_to_float(uint32_t w)
 {
+#if JSDR_FFT_CVT
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+#else
     w ^= 0x80008000u;
     const float2 b = make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
                                  __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)));
     if constexpr (PACK) return cadd(b, make_float2(-8421376.0f, -8421376.0f));
     else return make_float2(b.x - 8421376.0f, b.y - 8421376.0f);
+#endif
 }
 
 template <class P, int IN>

@@ -221,9 +221,9 @@ def test_bpsk_decimator_impulse_response_is_taps():
 
 
 def test_s16_division_shortcut_is_exact_for_every_input():
-    """The CUDA ingest computes (float)s/32767f as q0 = s*r, e = fma(-q0, 32767, s),
-    q = fma(r, e, q0) with r = fl(1/32767) (csrc/bpsk.cu s16_over_32767).  It must equal
-    the IEEE division of JavaAudio.java:283 for all 65536 inputs (exact rational check)."""
+    """The CUDA ingest computes (float)s/32767f as fma(s, r_hi, s*r_lo) with r_hi + r_lo the
+    two-float split of 1/32767 (csrc/bpsk.cu s16_over_32767, csrc/bpsk_stream.cuh).  It must
+    equal the IEEE division of JavaAudio.java:283 for all 65536 inputs (exact rational check)."""
     from fractions import Fraction
     f32 = np.float32
 
@@ -238,14 +238,15 @@ def test_s16_division_shortcut_is_exact_for_every_input():
                 best = (err, cand)
         return best[1]
 
-    r = f32(3.0518509447574615e-05)
-    assert r == f32(1.0) / f32(32767.0)
-    fr_r = Fraction(float(r))
+    r_hi = f32(3.0518509447574615e-05)
+    r_lo = f32(2.8422576792141996e-14)
+    assert r_hi == f32(1.0) / f32(32767.0)
+    assert r_lo == rnd32(Fraction(1, 32767) - Fraction(float(r_hi)))
+    fr_hi, fr_lo = Fraction(float(r_hi)), Fraction(float(r_lo))
     for x in range(-32768, 32768):
         xf = Fraction(x)
-        q0 = rnd32(xf * fr_r)
-        e = rnd32(xf - Fraction(float(q0)) * 32767)
-        q = rnd32(Fraction(float(q0)) + fr_r * Fraction(float(e)))
+        t = rnd32(xf * fr_lo)
+        q = rnd32(xf * fr_hi + Fraction(float(t)))
         assert q == f32(x) / f32(32767.0), x
 
 
