@@ -331,7 +331,9 @@ def main():
     h_raw[:] = tile[np.arange(e_ch) % tile_ch]
     def e2e_step():
         J.pump_receive_s16(f_e, bank_e, h_raw, nblk, h_psd, h_pk, mem=J.MEM_HOST)   # H2D raw, D2H PSD inside
-        J._ck(J.lib().jsdr_bpsk_read_ds(bank_e.h, J._ptr(h_ds), J.MEM_HOST))         # D2H decimated output
+        # D2H of the decimated output on the download stream: it drains beside the next step's
+        # upload (PCIe is full duplex); the sync that closes the timed region waits for the last one
+        bank_e.read_ds_async(h_ds)
     for _ in range(2):
         e2e_step()
     barrier()

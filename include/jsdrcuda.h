@@ -164,6 +164,10 @@ int jsdr_bpsk_receive_s16(jsdr_bpsk *b, const int16_t *raw, int nsamples,
 /* what the last receive produced, per channel */
 int jsdr_bpsk_last_counts(jsdr_bpsk *b, int32_t *n_ds /* outputs per channel */);
 int jsdr_bpsk_read_ds(jsdr_bpsk *b, double *out /* nchan*n_ds*2 */, int mem);   /* fed to RxDemodulate */
+/* the same copy without the wait: it runs on the download stream behind the decimator, beside
+ * whatever is submitted next (the following block's upload); `out` holds the rows once
+ * jsdr_ctx_sync has returned.  The next receive orders itself behind the copy. */
+int jsdr_bpsk_read_ds_async(jsdr_bpsk *b, double *out /* nchan*n_ds*2 */, int mem);
 int jsdr_bpsk_read_dm(jsdr_bpsk *b, double *out /* nchan*n_ds*2 */, int mem);   /* matched filter fi,fq */
 /* bits are +1/-1 (the value written to dmFECCorr, :554); bit_at is the cntDS
  * index of the 9600 S/s sample the decision was taken on.  max_bits is the row

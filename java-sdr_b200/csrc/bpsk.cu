@@ -154,6 +154,9 @@ __device__ __forceinline__ double phase_step2(double p, double inc, double th1, 
 }
 
 constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
+// Dynamic shared memory a scout CTA asks for (and never uses): 2 x 90 KB fit one SM's 227 KB and
+// 3 do not; 90 KB fits beside two of the 67.6 KB CTAs of the N = 4096 FFT plan (fft_plans.h).
+constexpr int kScoutSmem = 90 * 1024;
 
 // CTA size of the phase scout = how many SMs it takes (one CTA each; the streaming data kernel
 // leaves them free when it runs beside it).  The replay runs at full speed with one warp per SM
@@ -863,8 +866,16 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
     jsdr_ctx *ctx = b->ctx;
     ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
     const int st = scout_threads(b);
-    k_tuner_scout<<<(b->nchan + st - 1) / st, st, 0, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
-                                                             b->nchan, S);
+    // The replay is a latency-bound chain that wants a sub-partition's FP64 pipe to itself, and
+    // CTAs of a high-priority stream are placed wherever a slot frees up: sixteen of these small
+    // CTAs fit in the space one retiring data CTA leaves, and stacked like that they run nine
+    // times slower.  A shared-memory request the kernel never touches bounds the stacking: at
+    // most two per SM, one in the hole an FFT CTA leaves (kScoutSmem, see there).
+    static PerDeviceFlag attr_done;
+    if (!attr_done.test_and_set(ctx->device))
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoutSmem));
+    k_tuner_scout<<<(b->nchan + st - 1) / st, st, kScoutSmem, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+                                                                      b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
     P.S = S;
@@ -1065,6 +1076,10 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
+    if (b->ds_read_pending) {      // an asynchronous read of the previous block's output is still draining
+        JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_ds_read, 0));
+        b->ds_read_pending = 0;
+    }
     b->last_nds = 0;
     if (S == 0) {
         JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * b->nchan, ctx->aux));
@@ -1378,6 +1393,8 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     cudaStreamSynchronize(b->ctx->aux);
     if (b->ev_dm_ready) cudaEventDestroy(b->ev_dm_ready);
     if (b->ev_vco_ready) cudaEventDestroy(b->ev_vco_ready);
+    if (b->ev_ds_ready) cudaEventDestroy(b->ev_ds_ready);
+    if (b->ev_ds_read) cudaEventDestroy(b->ev_ds_read);
     for (int i = 0; i < 2; i++)
         if (b->ev_bits_done[i]) cudaEventDestroy(b->ev_bits_done[i]);
     void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
@@ -1500,6 +1517,31 @@ int read_rows(jsdr_bpsk *b, const double2 *src, double *out, int mem)
 }  // namespace
 
 extern "C" int jsdr_bpsk_read_ds(jsdr_bpsk *b, double *out, int mem) { return read_rows(b, b ? b->d_ds_out : nullptr, out, mem); }
+
+// The same rows, copied on the download stream behind the decimator and without waiting: the
+// copy overlaps whatever the caller submits next (the upload of the following block, in the
+// pump); jsdr_ctx_sync -- or the next synchronous read -- completes it.
+extern "C" int jsdr_bpsk_read_ds_async(jsdr_bpsk *b, double *out, int mem)
+{
+    JSDR_REQUIRE(b && out, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
+    jsdr_ctx *ctx = b->ctx;
+    JSDR_TRY(ctx->bind());
+    if (!b->ev_ds_ready) {
+        JSDR_CUDA(cudaEventCreateWithFlags(&b->ev_ds_ready, cudaEventDisableTiming));
+        JSDR_CUDA(cudaEventCreateWithFlags(&b->ev_ds_read, cudaEventDisableTiming));
+    }
+    if (b->last_nds == 0) return JSDR_OK;
+    JSDR_CUDA(cudaEventRecord(b->ev_ds_ready, ctx->stream));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_out, b->ev_ds_ready, 0));
+    JSDR_CUDA(cudaMemcpy2DAsync(out, sizeof(double2) * b->last_nds, b->d_ds_out, sizeof(double2) * b->max_ds,
+                                sizeof(double2) * b->last_nds, b->nchan,
+                                mem == JSDR_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                ctx->copy_out));
+    JSDR_CUDA(cudaEventRecord(b->ev_ds_read, ctx->copy_out));
+    b->ds_read_pending = 1;
+    return JSDR_OK;
+}
 
 extern "C" int jsdr_bpsk_read_dm(jsdr_bpsk *b, double *out, int mem)
 {

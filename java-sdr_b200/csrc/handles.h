@@ -94,6 +94,9 @@ struct jsdr_bpsk {
     bool vco_ahead_valid = false;    // the replay of the NEXT block is already on the side stream
     int vco_ahead_NO = 0, vco_ahead_kb = 0;
     cudaEvent_t ev_vco_ready = nullptr;
+    // jsdr_bpsk_read_ds_async: decimator done -> copy stream, copy done -> next block's decimator
+    cudaEvent_t ev_ds_ready = nullptr, ev_ds_read = nullptr;
+    int ds_read_pending = 0;
     // The bit-timing stage (and the frame stage behind it) runs on the context's auxiliary stream,
     // beside the next block's tuner / matched filter on the main stream.  What it reads is therefore
     // double buffered: matched-filter output, VCO table indices and bit-phase roll-overs of block k

@@ -94,6 +94,7 @@ _SIGS = {
     "jsdr_bpsk_receive_s16": [_vp, _vp, _i, _i64, _i, _i, _i],
     "jsdr_bpsk_last_counts": [_vp, C.POINTER(C.c_int32)],
     "jsdr_bpsk_read_ds": [_vp, _vp, _i],
+    "jsdr_bpsk_read_ds_async": [_vp, _vp, _i],
     "jsdr_bpsk_read_dm": [_vp, _vp, _i],
     "jsdr_bpsk_read_bits": [_vp, _vp, _vp, _vp, _i, _i],
     "jsdr_bpsk_read_counters": [_vp, _vp],
@@ -129,7 +130,11 @@ def lib() -> C.CDLL:
         # JSDR_LIB: another build of the same library (kernel experiments, tools/kbench.py)
         _lib = C.CDLL(os.environ.get("JSDR_LIB") or _SO)
         for name, args in _SIGS.items():
-            fn = getattr(_lib, name)
+            fn = getattr(_lib, name, None)
+            if fn is None:
+                if os.environ.get("JSDR_LIB"):      # an older experiment build may lack newer entry points
+                    continue
+                raise ImportError(f"{_SO} does not export {name}: rebuild it")
             fn.argtypes = args
             fn.restype = C.c_int
         _lib.jsdr_last_error.restype = C.c_char_p
@@ -492,6 +497,15 @@ class FUNcubeBPSKDemod:
         out = np.empty((self.nchan, n, 2), dtype=np.float64)
         _ck(lib().jsdr_bpsk_read_ds(self.h, _ptr(out), MEM_HOST))
         return out
+
+    def read_ds_async(self, out: np.ndarray) -> int:
+        """Start the copy of the decimated rows into `out` (pinned host memory, at least
+        nchan x last_nds x 2 doubles) and return last_nds at once; the rows are there after
+        Context.sync().  The copy overlaps the next block's upload."""
+        n = self.last_nds()
+        assert out.dtype == np.float64 and out.size >= self.nchan * n * 2
+        _ck(lib().jsdr_bpsk_read_ds_async(self.h, _ptr(out), MEM_HOST))
+        return n
 
     def read_dm(self) -> np.ndarray:
         n = self.last_nds()

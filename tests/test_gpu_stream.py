@@ -141,6 +141,33 @@ def test_pump_host_path_chunked_equals_separate_handlers(ctx):
         h.close()
 
 
+def test_async_ds_read_equals_blocking_read_and_orders_the_next_block(ctx):
+    """jsdr_bpsk_read_ds_async copies on the download stream without waiting; the rows must
+    equal the blocking read's, also when the next block is submitted straight behind it
+    (that block's decimator has to wait for the copy before it overwrites the device rows)."""
+    rate, nchan, S = 192000, 96, 8192
+    rng = np.random.default_rng(5)
+    tun = rng.uniform(2000, 90000, nchan)
+    adsc = J.AudioDescriptor(rate)
+    a = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=S, stages=1)
+    b = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=S, stages=1)
+    outs = [ctx.host_alloc((nchan * (S // 20 + 1) * 2,), np.float64) for _ in range(3)]
+    raws = [rng.integers(-30000, 30000, (nchan, 2 * S)).astype(np.int16) for _ in range(3)]
+    want, counts = [], []
+    for k in range(3):
+        a.receive_raw(raws[k])
+        want.append(a.read_ds())
+        b.receive_raw(raws[k])
+        counts.append(b.read_ds_async(outs[k]))     # no wait: the next receive follows at once
+    ctx.sync()
+    for k in range(3):
+        n = counts[k]
+        assert n == want[k].shape[1]
+        assert np.array_equal(outs[k][: nchan * n * 2].reshape(nchan, n, 2), want[k]), k
+    a.close()
+    b.close()
+
+
 def test_full_size_bank_stream_equals_tile_and_is_linear(ctx):
     """BASELINE config 4's full bank (4096 channels, 192 kS/s, 64 taps, D=20) on 32768-sample
     blocks: the streaming kernel (every SM, several segments per channel, phase checkpoints

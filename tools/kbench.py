@@ -122,11 +122,46 @@ def chain(nchan=4096, S=131072, rate=192000):
     ctx.close()
 
 
+def pump(nchan=4096, nblk=128, n=4096, rate=192000, reps=6):
+    """BASELINE config 5's step (FFT + PSD per block, tuner + 64-tap decimator) through
+    jsdr_pump_receive_s16 with device buffers: step time and per-kernel event times."""
+    ctx = J.Context(0)
+    S = nblk * n
+    rng = np.random.default_rng(3)
+    tun = rng.uniform(2000, 90000, nchan)
+    d_raw = ctx.dev_alloc(nchan * S * 4)
+    tile = rng.integers(-20000, 20000, (16, 2 * S)).astype(np.int16)
+    for c0 in range(0, nchan, 16):
+        d_raw.upload(tile[: min(16, nchan - c0)], offset=c0 * S * 4)
+    adsc = J.AudioDescriptor(rate)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=S, stages=1)
+    bank.set_ds_filter(J.design_lowpass(64, 4800.0, rate))
+    f = J.fft(ctx, None, adsc, max_batch=nchan * nblk, n=n)
+    d_psd = ctx.dev_alloc(nchan * nblk * (n + 2) * 4)
+    d_pk = ctx.dev_alloc(nchan * nblk * 4)
+    step = lambda: J.pump_receive_s16(f, bank, d_raw, nblk, d_psd, d_pk, mem=J.MEM_DEVICE)
+    for _ in range(3):
+        step()
+    ctx.sync()
+    ctx.profile(True)
+    ctx.timer_start()
+    for _ in range(reps):
+        step()
+    ms = ctx.timer_stop_ms() / reps
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    per = {k: round(v[0] / max(v[1], 1), 3) for k, v in prof.items() if v[1]}
+    print(f"pump nchan={nchan} nblk={nblk} n={n}: {ms:8.3f} ms/step  {nchan * S / ms / 1e3:9.1f} Msamples/s  per-kernel ms {per}", flush=True)
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mix"
     if what == "mix":
         a = [int(x) for x in sys.argv[2:]]
         mix(*a)
+    elif what == "pump":
+        pump(*[int(x) for x in sys.argv[2:]])
     elif what == "chain":
         chain(*[int(x) for x in sys.argv[2:]])
     else:
