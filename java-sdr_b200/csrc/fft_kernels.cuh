@@ -314,7 +314,10 @@ struct Plan {
     // hide the load phase behind other CTAs' butterflies.  Those plans run persistent CTAs that
     // fetch the next block's pass-0 samples into registers before the last pass of the current
     // one (s16 input: one register per sample).
-    static constexpr bool PERSIST = (G_ == 1) && (N_ >= 9600);
+#ifndef JSDR_FFT_NO_PERSIST
+#define JSDR_FFT_NO_PERSIST 0
+#endif
+    static constexpr bool PERSIST = !JSDR_FFT_NO_PERSIST && (G_ == 1) && (N_ >= 9600) && (SMEM > 113 * 1024);   // only one CTA fits an SM
     // CTAs per SM the kernel is compiled for: what shared memory allows, at the register budget
     // the largest register DFT needs.  Radix <= 16 fits 48 registers (4096 = 16^3 then keeps five
     // CTAs per SM instead of slipping to four); radix 32 fits 80, and a 256-thread CTA at 81..88
@@ -438,7 +441,10 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 
     const int tid = threadIdx.x;
     constexpr int N = P::N;
-    constexpr bool PREFETCH = P::PERSIST && IN == IN_S16;
+    // persistent only where the register prefetch exists (s16 input: one register per sample);
+    // float input keeps one CTA per block and the L2 prefetch (measured: 0.50 -> 0.61 at 16384)
+    constexpr bool PERSIST = P::PERSIST && IN == IN_S16;
+    constexpr bool PREFETCH = PERSIST;
 
     // pass-0 samples of the next block (persistent plans, s16 input)
     uint32_t pre[PREFETCH ? P::PRE_IT : 1][PREFETCH ? P::R0 : 1];
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
     // then wait for L2 instead of HBM (the few resident CTAs of the large-radix plans cannot hide
     // an HBM round trip behind each other).  Only the 16-byte-aligned interior of the range is
     // touched, and only whole groups inside the batch.
-    if constexpr (!P::PERSIST) {
+    if constexpr (!PERSIST) {
         if (tid == 0 && a.pf_dist > 0) {
             const long nb = blk0 + (long)a.pf_dist * P::G;
             if (nb + P::G <= a.nblocks) {
@@ -679,7 +685,7 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             }
         }
     }
-    if constexpr (!P::PERSIST) break;
+    if constexpr (!PERSIST) break;
     __syncthreads();                             // shared memory and s_max/s_idx are reused by the next block
     blk0 += blk_step;
     } while (blk0 < a.nblocks);
