@@ -56,6 +56,8 @@ public final class JsdrCuda {
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_INT));
 	static final MethodHandle BPSK_READ_BITS = h("jsdr_bpsk_read_bits",
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+	static final MethodHandle PUMP_RECEIVE_S16 = h("jsdr_pump_receive_s16",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
 	static final MethodHandle BPSK_READ_DS_ASYNC = h("jsdr_bpsk_read_ds_async",
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
 	static final MethodHandle BPSK_READ_COUNTERS = h("jsdr_bpsk_read_counters",
