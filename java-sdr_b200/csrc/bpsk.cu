@@ -1608,13 +1608,7 @@ int pump_fft(void *user, const void *d_in)
 {
     PumpJob *j = static_cast<PumpJob *>(user);
     jsdr_ctx *ctx = j->f->ctx;
-    static int on_aux = -1;                             // (experiment) JSDR_PUMP_FFT_AUX=1: the FFT on the low-priority stream
-    if (on_aux < 0) {
-        const char *e = getenv("JSDR_PUMP_FFT_AUX");
-        on_aux = e ? atoi(e) != 0 : 0;
-    }
-    return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc,
-                       on_aux ? ctx->aux : ctx->stream);
+    return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream);
 }
 }  // namespace
 
