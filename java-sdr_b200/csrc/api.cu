@@ -67,6 +67,7 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
         const int mid = (hi < lo) ? lo - 1 : lo;
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mid));
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi));
+        JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->side2, cudaStreamNonBlocking, hi));
         JSDR_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, lo));
     }
     JSDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -91,6 +92,7 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
     ctx->bind();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
+    cudaStreamSynchronize(ctx->side2);
     cudaEventDestroy(ctx->ev_t0);
     cudaEventDestroy(ctx->ev_t1);
     cudaEventDestroy(ctx->ev_aux_fork);
@@ -111,6 +113,7 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
     cudaStreamDestroy(ctx->copy_out);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->side);
+    cudaStreamDestroy(ctx->side2);
     delete ctx;
     return JSDR_OK;
 }
@@ -120,6 +123,7 @@ extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaStreamSynchronize(ctx->side));
+    JSDR_CUDA(cudaStreamSynchronize(ctx->side2));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     JSDR_CUDA(cudaStreamSynchronize(ctx->aux));

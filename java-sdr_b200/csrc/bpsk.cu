@@ -892,12 +892,17 @@ int launch_vco_scout(jsdr_bpsk *b, int NO, int kb)
     const double vco_inc = 2.0 * M_PI * 1200.0 / (double)9600;      // :88
     const double bit_inc = 1.0 / (double)9600, bit_time = 1.0 / (double)1200;   // :91-92
     // (the bit-timing kernel of two blocks ago may still be reading this buffer)
-    if (b->bits_used[kb]) JSDR_CUDA(cudaStreamWaitEvent(ctx->side, b->ev_bits_done[kb], 0));
+    // Own stream: a one-CTA serial chain of about a third of the tuner scout's length; behind that
+    // scout on the same stream it made the side stream the critical path of the whole chain.
+    if (b->bits_used[kb]) JSDR_CUDA(cudaStreamWaitEvent(ctx->side2, b->ev_bits_done[kb], 0));
+    // (and the matched filter that last read this buffer, two blocks ago, is done: the event is the
+    // newer one of the previous block)
+    if (b->ev_dm_ready) JSDR_CUDA(cudaStreamWaitEvent(ctx->side2, b->ev_dm_ready, 0));
     const int c = b->vco_state_cur;
-    k_vco_scout<<<1, 64, 0, ctx->side>>>(b->d_vco_state + 2 * c, b->d_vco_state + 2 * (c ^ 1), b->d_vco_ix[kb],
+    k_vco_scout<<<1, 64, 0, ctx->side2>>>(b->d_vco_state + 2 * c, b->d_vco_state + 2 * (c ^ 1), b->d_vco_ix[kb],
                                          b->d_bit_roll[kb], NO, vco_inc, bit_inc, bit_time);
     JSDR_TRY(launched(ctx, "k_vco_scout"));
-    JSDR_CUDA(cudaEventRecord(b->ev_vco_ready, ctx->side));
+    JSDR_CUDA(cudaEventRecord(b->ev_vco_ready, ctx->side2));
     return JSDR_OK;
 }
 
@@ -1099,6 +1104,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     if (autotune) JSDR_REQUIRE(S == b->max_block, JSDR_EINVAL, "auto-tune needs whole blocks of max_block_samples");
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     JSDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    JSDR_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
     if (!autotune && !(P.valid && P.S == S)) JSDR_TRY(launch_scout(b, P, S));
     const int kb = b->bit_cur;                         // buffer of the 9600 S/s stages for this block
     if (b->stages >= 2 && NO > 0) {
@@ -1389,6 +1395,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     if (!b) return JSDR_OK;
     b->ctx->bind();
     cudaStreamSynchronize(b->ctx->side);
+    cudaStreamSynchronize(b->ctx->side2);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStreamSynchronize(b->ctx->aux);
     if (b->ev_dm_ready) cudaEventDestroy(b->ev_dm_ready);
@@ -1460,6 +1467,7 @@ extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
     JSDR_TRY(b->ctx->bind());
     // the scout may be running ahead with the old increment: let it finish and drop its plan
     JSDR_CUDA(cudaStreamSynchronize(b->ctx->side));
+    JSDR_CUDA(cudaStreamSynchronize(b->ctx->side2));
     b->plan[0].valid = b->plan[1].valid = false;
     b->h_tuning[chan] = hz;
     double inc = 2.0 * M_PI * hz / (double)b->rate;       // :188

@@ -51,6 +51,7 @@ struct jsdr_ctx {
     int l2_prefetch = 1;             // FFT: bulk-prefetch a later CTA's input into L2 (JSDR_L2_PREFETCH=0 turns it off)
     cudaStream_t stream = nullptr;   // main stream: data kernels
     cudaStream_t side = nullptr;     // side stream: data-independent phase scouts
+    cudaStream_t side2 = nullptr;    // the VCO / bit-phase replay: one short serial chain, beside the tuner scout
     cudaStream_t aux = nullptr;      // low priority: work that runs beside the main stream's kernel
     cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies of the chunked host path
