@@ -1398,6 +1398,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     cudaStreamSynchronize(b->ctx->side2);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStreamSynchronize(b->ctx->aux);
+    if (b->ds_read_pending) cudaStreamSynchronize(b->ctx->copy_out);   // an asynchronous read may still be draining
     if (b->ev_dm_ready) cudaEventDestroy(b->ev_dm_ready);
     if (b->ev_vco_ready) cudaEventDestroy(b->ev_vco_ready);
     if (b->ev_ds_ready) cudaEventDestroy(b->ev_ds_ready);
