@@ -363,19 +363,32 @@ __device__ __forceinline__ float lg2_approx(float x)
     return r;
 }
 
-// exact s16 pair -> float pair.  CVT: one I2F.S16 per half on the conversion (XU) pipe -- two
-// instructions and nothing on the FMA pipe, which is the one this kernel saturates.  Otherwise
-// (the default; -DJSDR_FFT_CVT=1 selects the I2F form, measured 2-3% slower: it shares the XU pipe with MUFU.LG2): bias to unsigned, splice into the mantissa
-// of 2^23, subtract 2^23 + 32768 with one FADD2.  The 1/32767 of JavaAudio.java:283 is folded
-// into cf (the transform is linear).
+// exact s16 pair -> float pair; three forms, chosen at build time (-DJSDR_FFT_CVT=n):
+//   2 (default)  sign-extend on the ALU (PRMT with sign replication / arithmetic shift) and
+//                I2FP.F32.S32: four instructions per pair and nothing on the FMA pipe, the one
+//                this kernel saturates (0.5-2 % faster than form 0);
+//   1            I2F.S16 straight from the halves: two instructions, but on the XU pipe next to
+//                MUFU.LG2 (2-3 % slower than form 0);
+//   0            bias to unsigned, splice into the mantissa of 2^23, subtract 2^23 + 32768 with
+//                one FADD2.
+// The 1/32767 of JavaAudio.java:283 is folded into cf (the transform is linear).
 #ifndef JSDR_FFT_CVT
-#define JSDR_FFT_CVT 0
+#define JSDR_FFT_CVT 2
 #endif
 template <bool PACK>
 __device__ __forceinline__ float2 s16_bits_to_float(uint32_t w)
 {
-#if JSDR_FFT_CVT
+#if JSDR_FFT_CVT == 1
     return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+#elif JSDR_FFT_CVT == 2
+    // sign-extend on the ALU (PRMT with sign replication, arithmetic shift), I2FP.F32.S32
+    // (prmt in PTX: selector bit 3 replicates the chosen byte's sign; __byte_perm masks it off)
+    float a, b;
+    int lo;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(w));
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(a) : "r"(lo));
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(b) : "r"((int)w >> 16));
+    return make_float2(a, b);
 #else
     w ^= 0x80008000u;
     const float2 b = make_float2(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)),
