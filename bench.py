@@ -141,7 +141,7 @@ class ClockSampler:
         t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
         rows = [(ts, r) for ts, r in self.rows if t0 is None or t0 <= ts <= t1]
         scope = "timed region"
-        if not rows:    # too short a region for the sampling period: everything since before the warm-up
+        if len(rows) < 3:   # too short a region for nvidia-smi's sampling period: everything since before the warm-up
             rows, scope = self.rows, "warm-up + timed region"
         for ts, r in rows:
             try:
