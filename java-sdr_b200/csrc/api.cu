@@ -1,4 +1,5 @@
 // api.cu — context, memory and timing entry points of libjsdrcuda.so.
+#include <algorithm>
 #include <cstdlib>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -57,7 +58,7 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     jsdr_ctx *ctx = new jsdr_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char *e = getenv("JSDR_L2_PREFETCH")) ctx->l2_prefetch = atoi(e) != 0;
+    if (const char *e = getenv("JSDR_L2_PREFETCH")) ctx->l2_prefetch = std::max(0, std::min(atoi(e), 8));   // 0: off, n: n x resident CTAs ahead
     {   // three priorities: the side stream carries the serial, data-independent phase replay and
         // goes first, so that its few CTAs are placed as soon as a slot frees up instead of queueing
         // behind the whole grid of a data kernel; the main stream is in the middle; the auxiliary

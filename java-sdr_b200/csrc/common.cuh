@@ -48,7 +48,7 @@ struct jsdr_prof_span {
 struct jsdr_ctx {
     int device = 0;
     int sm_count = 0;
-    int l2_prefetch = 1;             // FFT: bulk-prefetch a later CTA's input into L2 (JSDR_L2_PREFETCH=0 turns it off)
+    int l2_prefetch = 1;             // FFT: bulk-prefetch the input of the CTA n x (resident CTAs) ahead into L2 (JSDR_L2_PREFETCH=n, 0: off)
     cudaStream_t stream = nullptr;   // main stream: data kernels
     cudaStream_t side = nullptr;     // side stream: data-independent phase scouts
     cudaStream_t side2 = nullptr;    // the VCO / bit-phase replay: one short serial chain, beside the tuner scout

@@ -24,7 +24,7 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
     }
     Args b = a;
     if constexpr (P::PERSIST && IN == IN_S16) grid = std::min(grid, per_sm * ctx->sm_count);   // resident CTAs loop over the blocks
-    else b.pf_dist = ctx->l2_prefetch ? per_sm * ctx->sm_count : 0;            // L2 look-ahead distance in CTAs
+    else b.pf_dist = ctx->l2_prefetch * per_sm * ctx->sm_count;                // L2 look-ahead distance in CTAs
     ProfScope prof(ctx, JSDR_K_FFT, st);
     kern<<<grid, P::T, P::SMEM, st>>>(b);
     return launched(ctx, "fft_kernel");
