@@ -154,9 +154,11 @@ __device__ __forceinline__ double phase_step2(double p, double inc, double th1, 
 }
 
 constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
-// Dynamic shared memory a scout CTA asks for (and never uses): 2 x 90 KB fit one SM's 227 KB and
-// 3 do not; 90 KB fits beside two of the 67.6 KB CTAs of the N = 4096 FFT plan (fft_plans.h).
-constexpr int kScoutSmem = 90 * 1024;
+// Dynamic shared memory a scout CTA asks for (and never uses): more than half an SM's 227 KB, so
+// that two scout CTAs can never share an SM (at 90 KB two did when an SM emptied -- a 1024-channel
+// bank ran its replay in 7.4 ms instead of 6.0); what is left still takes one 67.6 KB CTA of
+// the N = 4096 FFT plan beside it.  JSDR_SCOUT_SMEM_KB overrides it (tuning aid).
+constexpr int kScoutSmem = 116 * 1024;
 
 // CTA size of the phase scout = how many SMs it takes (one CTA each; the streaming data kernel
 // leaves them free when it runs beside it).  The replay runs at full speed with one warp per SM
@@ -869,12 +871,17 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
     // The replay is a latency-bound chain that wants a sub-partition's FP64 pipe to itself, and
     // CTAs of a high-priority stream are placed wherever a slot frees up: sixteen of these small
     // CTAs fit in the space one retiring data CTA leaves, and stacked like that they run nine
-    // times slower.  A shared-memory request the kernel never touches bounds the stacking: at
-    // most two per SM, one in the hole an FFT CTA leaves (kScoutSmem, see there).
+    // times slower.  A shared-memory request the kernel never touches rules the stacking out:
+    // one scout CTA per SM (kScoutSmem, see there).
+    static int scout_smem = 0;
+    if (!scout_smem) {
+        const char *e = getenv("JSDR_SCOUT_SMEM_KB");          // (tuning aid)
+        scout_smem = e ? std::max(1, std::min(atoi(e), 200)) * 1024 : kScoutSmem;
+    }
     static PerDeviceFlag attr_done;
     if (!attr_done.test_and_set(ctx->device))
-        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoutSmem));
-    k_tuner_scout<<<(b->nchan + st - 1) / st, st, kScoutSmem, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
+    k_tuner_scout<<<(b->nchan + st - 1) / st, st, scout_smem, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
                                                                       b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
