@@ -285,6 +285,16 @@ def main():
     mix_ms = kern["mixdecim"][0] / max(kern["mixdecim"][1], 1)
     scout_ms = kern["scout"][0] / max(kern["scout"][1], 1)
 
+    # ---- the FFT kernel with the SMs to itself (no phase scout beside it), for the record
+    ctx.sync()
+    for _ in range(2):
+        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(5):
+        f.receive_dev(d_raw, batch, d_psd, d_peak, s16=True)
+    fft_alone_ms = ctx.timer_stop_ms() / 5
+
     # ---- the other decimator arithmetic, same pipeline, for the record (rank-local, few steps)
     other = "f32" if a.precision == "f64" else "f64"
     bank.set_precision(J.PREC_F32 if other == "f32" else J.PREC_F64)
@@ -393,6 +403,11 @@ def main():
                          "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                          "ms_per_launch": dom["ms_per_launch"],
                          "timing": "CUDA events around each launch on its own stream, averaged over the timed region",
+                         "fft_kernel_alone": {"ms_per_launch": round(fft_alone_ms, 4),
+                                              "achieved": round(fft_bytes / (fft_alone_ms * 1e-3) / 1e9, 1),
+                                              "frac": round(fft_bytes / (fft_alone_ms * 1e-3) / 1e9 / peak, 4),
+                                              "note": "same launch outside the pipeline (rank 0): in the step it shares 32 SMs "
+                                                      "with the phase scout of the next block"},
                          "other_kernels": kernels[1:] + [{"kernel": "k_tuner_scout (exact tuner phase replay, side stream, overlapped)",
                                                           "ms_per_launch": round(scout_ms, 4)}],
                          "pipeline": {"algorithmic_bytes_per_step_fused": step_bytes,
