@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define JSDR_ABI_VERSION 1
+#define JSDR_ABI_VERSION 2
 
 typedef enum jsdr_status {
     JSDR_OK = 0,
@@ -246,15 +246,31 @@ int jsdr_fir_filter_i32(jsdr_fir *f, const int32_t *in, int nsamples, int64_t ch
 int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const int32_t *b, int32_t *out,
                              int64_t npairs, int mem);
 
+/* ------------------------------------------------------------- constant tables
+ * The constants the library builds for itself, readable without a device so that the
+ * reference-pinning tests can compare EVERY entry with the literals of the Java sources:
+ *   jsdr_probe_table  which = 0 Partab[256] (FECDecoder.java:40-57), 1 Syms[128] (:105-114),
+ *                     2 Scrambler[320] (:118-139), 3 ALPHA_TO[256] (:145-162),
+ *                     4 INDEX_OF[256] (:164-181), 5 RS_poly[16] (:544-546),
+ *                     6 SYNC_VECTOR[65] (FUNcubeBPSKDemod.java:79-81); first n entries
+ *   jsdr_probe_taps   dsFilter[27] (FUNcubeBPSKDemod.java:27-55) and the 65 distinct taps of
+ *                     dmFilter (:58-77, stored twice there)
+ */
+int jsdr_probe_table(int which, int32_t *out, int n);
+int jsdr_probe_taps(double ds27[27], double dm65[65]);
+
 /* ------------------------------------------------------------------ the pump
  * JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: every channel's
- * block goes to the fft handler and to the tuner bank in one call, the two
- * running concurrently on the device.  raw is [nchan][nblocks*n] s16 IQ; psd is
+ * block goes to the fft handler and to the tuner bank in one call: the FFT + PSD of every
+ * block, then the tuner bank over the same resident input, on one stream (the tuner-phase
+ * replay of the NEXT call runs beside them on a side stream).  ic/qc are JavaAudio's I/Q
+ * DC corrections (JavaAudio.java:281-288), applied to what both handlers see.
+ * raw is [nchan][nblocks*n] s16 IQ; psd is
  * [nchan][nblocks][n+2].  With mem == JSDR_MEM_HOST the copies are inside the
  * call (this is bench.py's e2e path).
  */
 int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
-                          float *psd, int32_t *peak_bin, int mem);
+                          int ic, int qc, float *psd, int32_t *peak_bin, int mem);
 
 #ifdef __cplusplus
 }

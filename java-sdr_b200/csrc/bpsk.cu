@@ -1631,7 +1631,7 @@ int pump_fft(void *user, const void *d_in)
 // JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: each channel's
 // blocks go to the fft handler and to the tuner bank.
 extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
-                                     float *psd, int32_t *peak_bin, int mem)
+                                     int ic, int qc, float *psd, int32_t *peak_bin, int mem)
 {
     JSDR_REQUIRE(f && b && raw && psd, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(f->ctx == b->ctx, JSDR_EINVAL, "handlers belong to different contexts");
@@ -1645,14 +1645,14 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     PumpJob job;
     job.f = f;
     job.batch = (int)batch;
-    job.ic = 0;
-    job.qc = 0;
+    job.ic = ic;                                   // JavaAudio.java:281-288: both handlers see the corrected samples
+    job.qc = qc;
     const size_t psd_elems = (size_t)batch * (f->n + 2);
     if (mem == JSDR_MEM_DEVICE) {
         job.d_psd = psd;
         job.d_peak = peak_bin;
         b->in_pump = 1;
-        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, 0, 0, mem, pump_fft, &job);
+        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, ic, qc, mem, pump_fft, &job);
         b->in_pump = 0;
         return rc;
     }
@@ -1688,7 +1688,7 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
         JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_in[c], ctx->copy_in));
         JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk_in[c], 0));
         JSDR_TRY(fft::launch(f, (const char *)b->d_in + in_off, fft::IN_S16, (int)nblk, f->d_out + blk0 * (f->n + 2),
-                             f->d_peak + blk0, fft::OUT_PSD, 0, 0, ctx->stream));
+                             f->d_peak + blk0, fft::OUT_PSD, ic, qc, ctx->stream));
         JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_done[c], ctx->stream));
         JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_chunk_done[c], 0));
         JSDR_CUDA(cudaMemcpyAsync(psd + blk0 * (f->n + 2), f->d_out + blk0 * (f->n + 2), nblk * (f->n + 2) * sizeof(float),
@@ -1698,10 +1698,22 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
                                       cudaMemcpyDeviceToHost, ctx->copy_out));
     }
     b->in_pump = 1;
-    const int rc_bank = bpsk_receive<FMT_S16>(b, b->d_in, (int)S, S, 0, 0, JSDR_MEM_DEVICE);
+    const int rc_bank = bpsk_receive<FMT_S16>(b, b->d_in, (int)S, S, ic, qc, JSDR_MEM_DEVICE);
     b->in_pump = 0;
     JSDR_TRY(rc_bank);
     JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JSDR_OK;
+}
+
+// The decimator and matched-filter taps as the kernels use them ((double)(float) of the
+// F-suffixed literals, FUNcubeBPSKDemod.java:27-77), for the reference-pinning tests
+// (tests/test_ref_tables.py compares every entry with the literals parsed from the Java source).
+// Host only: no device needed.
+extern "C" int jsdr_probe_taps(double *ds27, double *dm65)
+{
+    JSDR_REQUIRE(ds27 && dm65, JSDR_EINVAL, "null argument");
+    for (int i = 0; i < 27; i++) ds27[i] = (double)jsdr::bpsk::kDsFilterF[i];
+    for (int i = 0; i < 65; i++) dm65[i] = (double)jsdr::bpsk::kDmFilterF[i];
     return JSDR_OK;
 }

@@ -32,8 +32,11 @@ constexpr int ROWS = 80, COLS = 65;                           // interleaver (FE
 constexpr int SYMS = 5200, SYNC_LEN = 65, HIST = SYMS - 1;
 constexpr int CPOLYA = 0x4f, CPOLYB = 0x6d, SYNC_POLY = 0x48;
 
+// Generated from their defining polynomials; identical for every bank, so they are written to
+// the constant bank once per device and never again (the caller-supplied Viterbi metric table
+// lives in per-bank global memory instead: another bank's decode may be running when a bank is
+// enabled).
 struct Tables {
-    int16_t mettab[2][256];
     uint8_t partab[256];
     uint8_t syms[128];
     uint8_t scrambler[320];
@@ -51,9 +54,8 @@ __host__ __device__ static inline int mod255(int x)
     return x;
 }
 
-static void build_tables(Tables &t, const int16_t *mettab)
+static void build_tables(Tables &t)
 {
-    memcpy(t.mettab, mettab, sizeof(t.mettab));
     for (int i = 0; i < 256; i++) t.partab[i] = (uint8_t)parity8(i);
     // symbol pair of encoder state s; the second symbol is inverted (FECDecoder.java:105-114, 564)
     for (int s = 0; s < 128; s++) t.syms[s] = (uint8_t)((parity8(s & CPOLYA) << 1) | (1 - parity8(s & CPOLYB)));
@@ -93,6 +95,27 @@ static void build_tables(Tables &t, const int16_t *mettab)
     for (int i = 0; i < SYNC_LEN; i++) {
         t.sync[i] = (s7 & 64) ? 1 : -1;
         s7 = ((s7 << 1) | t.partab[s7 & SYNC_POLY]) & 0xff;
+    }
+}
+
+// The systematic RS encoder (:614-655) as a linear map: row i of par is the parity (x^32 * x^(127-i))
+// mod g(x) that a single 1 in data byte i of a block leaves, lowest-order parity byte first, so
+// the parity of a block is the GF(256) combination of the rows selected by its data bytes.
+// Row 127 is g(x) without its leading term; row i-1 is row i advanced by one zero byte.
+static void build_rs_parity_map(const Tables &t, uint8_t par[128][NROOTS])
+{
+    uint8_t g[NROOTS + 1];                                    // g[k], k = 1..32: palindromic, monic
+    for (int k = 1; k <= 16; k++) g[k] = t.alpha_to[t.rs_poly[k - 1]];
+    for (int k = 17; k < NROOTS; k++) g[k] = g[NROOTS - k];
+    g[NROOTS] = 1;
+    auto gmul = [&](int a, int b) { return (a && b) ? t.alpha_to[mod255(t.index_of[a] + t.index_of[b])] : 0; };
+    uint8_t reg[NROOTS];
+    for (int k = 0; k < NROOTS; k++) reg[k] = g[k + 1];
+    for (int i = 127; i >= 0; i--) {
+        memcpy(par[i], reg, NROOTS);
+        const int fb = reg[0];
+        for (int k = 0; k < NROOTS - 1; k++) reg[k] = (uint8_t)(reg[k + 1] ^ gmul(fb, g[k + 1]));
+        reg[NROOTS - 1] = (uint8_t)fb;
     }
 }
 
@@ -155,164 +178,196 @@ __global__ void __launch_bounds__(256) k_sync_shift(const int8_t *__restrict__ h
 }
 
 // ------------------------------------------------------------------ FECDecode, one warp per frame
+struct RsScratch {
+    uint8_t syn[NROOTS];          // S_i
+    uint8_t lam[NROOTS + 1];      // lambda coefficients (values)
+    uint8_t om[NROOTS];           // omega coefficients
+    uint8_t root[NROOTS], loc[NROOTS];
+};
+
 struct DecodeSmem {
     uint8_t raw[SYMS];                       // dmFECBits: 0xc0 / 0x40 (:564-566)
     uint8_t symbols[NBITS * 2 + 65 + 3];     // de-interleaved
     unsigned dec[NBITS][2];                  // decisions of states 2b (even) and 2b+1 (odd), bit b
     uint8_t vit[(NBITS - 6) / 8];
-    uint8_t rs[RSBLOCKS][NN];
+    uint8_t rs[RSBLOCKS][NN + 1];
     uint8_t out[256];
-    uint8_t reenc[SYMS];
+    uint8_t enc[324];                        // the 320 scrambled bytes the convolutional encoder sees, then zeros
+    int16_t mettab[2][256];                  // FECDecoder.java:67-100, the caller's copy (per bank)
+    uint8_t gf_exp2[512], gf_lg[256];
+    RsScratch rsw;
     int rserr[RSBLOCKS];
 };
 
-// decode_rs_8 (FECDecoder.java:325-519) with no erasures, one thread
-__device__ int decode_rs_8(uint8_t *data)
+// ---- GF(256) arithmetic on shared-memory tables (lane-divergent look-ups; the constant bank
+// would serialise them).  exp2[i] = alpha^i for i < 510 (two periods, so that the sum of two
+// logarithms needs no reduction), lg[v] = log_alpha v, lg[0] unused.
+struct GF {
+    const uint8_t *exp2, *lg;
+    __device__ __forceinline__ int mul(int a, int b) const { return (a && b) ? exp2[lg[a] + lg[b]] : 0; }
+    __device__ __forceinline__ int mul_exp(int a, int e) const { return a ? exp2[lg[a] + e] : 0; }   // a * alpha^e, e < 255
+    __device__ __forceinline__ int div(int a, int b) const { return a ? exp2[lg[a] + 255 - lg[b]] : 0; }   // b != 0
+};
+
+// RS(255,223) over GF(256), CCSDS roots alpha^(11*(112+i)), errors only — the whole warp decodes
+// one code word (FECDecoder.java:325-519 is the reference's sequential form of the same
+// mathematics; nothing of its structure is kept):
+//   syndromes        lane i evaluates the word at root i (Horner over the 160 stored symbols)
+//   Berlekamp-Massey lane l holds the coefficient lambda[l+1] and b[l]; the discrepancy is one
+//                    warp XOR-reduction, x*b(x) and lambda(x)/d are one shuffle
+//   root search      lane-parallel over the 255 field elements, roots compacted by ballot
+//   error values     lane i builds omega[i]; lane j evaluates Forney's quotient for root j
+// Returns what the reference returns: 0 for a clean word, the number of roots when
+// deg(lambda) roots were found and every derivative is non-zero, -1 otherwise.  The
+// Berlekamp-Massey recurrence is the textbook one the reference also runs, so lambda — and
+// with it the outcome for words with more than 16 errors — is the same polynomial.
+__device__ int rs_decode_warp(uint8_t *cw, RsScratch &R, const GF gf, int lane)
 {
-    int lambda[NROOTS + 1], s[NROOTS], b[NROOTS + 1], t[NROOTS + 1], omega[NROOTS + 1];
-    int root[NROOTS], reg[NROOTS + 1], loc[NROOTS];
-    int deg_lambda, el, deg_omega, count, r, syn_error;
-    const uint8_t *AT = c_tab.alpha_to, *IO = c_tab.index_of;
-    for (int i = 0; i <= NROOTS; i++) lambda[i] = 0;
-    for (int i = 0; i < NROOTS; i++) s[i] = data[0];
-    for (int j = 1; j < NN; j++)
-        for (int i = 0; i < NROOTS; i++) {
-            if (s[i] == 0) s[i] = data[j];
-            else s[i] = data[j] ^ AT[mod255(IO[s[i]] + (FCR + i) * PRIM)];
-        }
-    syn_error = 0;
-    for (int i = 0; i < NROOTS; i++) { syn_error |= s[i]; s[i] = IO[s[i]]; }
-    if (!syn_error) return 0;
-    lambda[0] = 1;
-    for (int i = 0; i < NROOTS + 1; i++) b[i] = IO[lambda[i]];
-    r = 0; el = 0;
-    while (++r <= NROOTS) {
-        int discr_r = 0;
-        for (int i = 0; i < r; i++)
-            if (lambda[i] != 0 && s[r - i - 1] != A0) discr_r ^= AT[mod255(IO[lambda[i]] + s[r - i - 1])];
-        discr_r = IO[discr_r];
-        if (discr_r == A0) {
-            for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
-            b[0] = A0;
+    const unsigned FULL = 0xffffffffu;
+    // ---- syndromes: S_i = cw(beta_i), beta_i = alpha^(PRIM*(FCR+i)); the 95 pad symbols are zero
+    {
+        const int be = ((FCR + lane) * PRIM) % NN;
+        int s = 0;
+        for (int j = RSPAD; j < NN; j++) s = cw[j] ^ gf.mul_exp(s, be);
+        R.syn[lane] = (uint8_t)s;
+        if (__ballot_sync(FULL, s != 0) == 0u) return 0;
+    }
+    __syncwarp();
+    // ---- Berlekamp-Massey.  lambda(x) = 1 + sum lam_l x^(l+1); b(x) = sum bq_l x^l
+    int lam = 0, bq = (lane == 0) ? 1 : 0, L = 0;
+    for (int r = 1; r <= NROOTS; r++) {
+        // discrepancy d = S[r-1] + sum_{i=1}^{r-1} lambda[i] S[r-1-i]
+        const int term = (lane <= r - 2) ? gf.mul(lam, R.syn[r - 2 - lane]) : 0;
+        const int d = __reduce_xor_sync(FULL, (unsigned)term) ^ R.syn[r - 1];
+        int b_up = __shfl_up_sync(FULL, bq, 1);              // x * b(x)
+        if (lane == 0) b_up = 0;
+        if (d == 0) {
+            bq = b_up;
         } else {
-            t[0] = lambda[0];
-            for (int i = 0; i < NROOTS; i++) {
-                if (b[i] != A0) t[i + 1] = lambda[i + 1] ^ AT[mod255(discr_r + b[i])];
-                else t[i + 1] = lambda[i + 1];
-            }
-            if (2 * el <= r - 1) {
-                el = r - el;
-                for (int i = 0; i <= NROOTS; i++) b[i] = (lambda[i] == 0) ? A0 : mod255(IO[lambda[i]] - discr_r + NN);
+            int l_up = __shfl_up_sync(FULL, lam, 1);         // coefficient `lane` of the old lambda
+            if (lane == 0) l_up = 1;
+            const int lam_new = lam ^ gf.mul(d, bq);         // lambda - d * x * b
+            if (2 * L <= r - 1) {
+                L = r - L;
+                bq = gf.div(l_up, d);                        // b = old lambda / d
             } else {
-                for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
-                b[0] = A0;
+                bq = b_up;
             }
-            for (int i = 0; i <= NROOTS; i++) lambda[i] = t[i];
+            lam = lam_new;
         }
     }
-    deg_lambda = 0;
-    for (int i = 0; i < NROOTS + 1; i++) {
-        lambda[i] = IO[lambda[i]];
-        if (lambda[i] != A0) deg_lambda = i;
-    }
-    for (int i = 1; i <= NROOTS; i++) reg[i] = lambda[i];
-    count = 0;
-    for (int i = 1, k = IPRIM - 1; i <= NN; i++, k = mod255(k + IPRIM)) {
+    const unsigned nz = __ballot_sync(FULL, lam != 0);
+    const int deg = nz ? 32 - __clz(nz) : 0;                  // highest non-zero coefficient
+    R.lam[lane + 1] = (uint8_t)lam;
+    if (lane == 0) R.lam[0] = 1;
+    __syncwarp();
+    // ---- roots of lambda among alpha^i, i = 1..255; error location of root i is (IPRIM*i - 1) mod 255
+    int count = 0;
+    for (int t = 0; t < 8; t++) {
+        const int i = 32 * t + lane + 1;
         int q = 1;
-        for (int j = deg_lambda; j > 0; j--)
-            if (reg[j] != A0) { reg[j] = mod255(reg[j] + j); q ^= AT[reg[j]]; }
-        if (q != 0) continue;
-        root[count] = i;
-        loc[count] = k;
-        if (++count == deg_lambda) break;
+        if (i <= NN) {
+            for (int j = 1; j <= deg; j++) q ^= gf.mul_exp(R.lam[j], (j * i) % NN);
+        }
+        const bool hit = (i <= NN) && (q == 0);
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (hit) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < NROOTS) {
+                R.root[pos] = (uint8_t)i;
+                R.loc[pos] = (uint8_t)((IPRIM * i - 1) % NN);
+            }
+        }
+        count += __popc(m);
     }
-    if (deg_lambda != count) return -1;
-    deg_omega = 0;
-    for (int i = 0; i < NROOTS; i++) {
-        int tmp = 0;
-        int j = (deg_lambda < i) ? deg_lambda : i;
-        for (; j >= 0; j--)
-            if (s[i - j] != A0 && lambda[j] != A0) tmp ^= AT[mod255(s[i - j] + lambda[j])];
-        if (tmp != 0) deg_omega = i;
-        omega[i] = IO[tmp];
+    if (count != deg) return -1;
+    // ---- omega(x) = S(x) lambda(x) mod x^32
+    {
+        int om = 0;
+        const int jm = min(deg, lane);
+        for (int j = 0; j <= jm; j++) om ^= gf.mul(R.syn[lane - j], R.lam[j]);
+        R.om[lane] = (uint8_t)om;
     }
-    omega[NROOTS] = A0;
-    for (int j = count - 1; j >= 0; j--) {
+    __syncwarp();
+    // ---- error values (Forney): lane j corrects location loc[j]
+    bool bad = false;
+    if (lane < count) {
+        const int rt = R.root[lane];
         int num1 = 0;
-        for (int i = deg_omega; i >= 0; i--)
-            if (omega[i] != A0) num1 ^= AT[mod255(omega[i] + i * root[j])];
-        const int num2 = AT[mod255(root[j] * (FCR - 1) + NN)];
-        int den = 0;
-        const int lim = deg_lambda < NROOTS - 1 ? deg_lambda : NROOTS - 1;
-        for (int i = lim & ~1; i >= 0; i -= 2)
-            if (lambda[i + 1] != A0) den ^= AT[mod255(lambda[i + 1] + i * root[j])];
-        if (den == 0) return -1;
-        if (num1 != 0) data[loc[j]] ^= AT[mod255(IO[num1] + IO[num2] + NN - IO[den])];
+        for (int i = 0; i < NROOTS; i++) num1 ^= gf.mul_exp(R.om[i], (i * rt) % NN);
+        int den = 0;                                          // lambda'(x) keeps the odd coefficients
+        for (int i = 0; i <= (min(deg, NROOTS - 1) & ~1); i += 2) den ^= gf.mul_exp(R.lam[i + 1], (i * rt) % NN);
+        if (den == 0) {
+            bad = true;
+        } else if (num1 != 0) {
+            const int num2e = (rt * (FCR - 1)) % NN;          // alpha^(root*(FCR-1))
+            cw[R.loc[lane]] ^= (uint8_t)gf.div(gf.mul_exp(num1, num2e), den);
+        }
     }
+    if (__any_sync(FULL, bad)) return -1;
+    __syncwarp();
     return count;
 }
 
-// encode_FEC40 (FECDecoder.java:527-688) into sym[5200] (0/1), one thread
-__device__ void encode_fec40(const uint8_t *data, uint8_t *sym)
+// Re-encoding for the channel-error count (FECDecoder.java:831-847 calls encode_FEC40, :527-688),
+// without building the 5200-symbol frame: the encoder is a fixed map from the 320 scrambled
+// bytes to frame positions, so every lane compares its own positions directly.
+//   RS parity   the systematic encoder is GF-linear: parity byte k of a block is the dot
+//               product of its 128 data bytes with column k of rs_par (x^(32+127-i) mod g(x),
+//               built on the host) — lane k owns parity byte k, no shift register
+//   symbols     frame position p = row*80 + col holds sync bit `row` in column 0 and otherwise
+//               encoder output number col*65 + row - 65: symbol (n & 1) of input bit n >> 1,
+//               a parity of the 7-bit window that ends at that bit
+__device__ int reencode_count_errors(const uint8_t *out, const uint8_t *raw, uint8_t *enc /* 322 */,
+                                     const uint8_t *__restrict__ rs_par, const GF gf, int lane)
 {
-    const uint8_t *AT = c_tab.alpha_to, *IO = c_tab.index_of, *PT = c_tab.partab;
-    int rs_block[RSBLOCKS][NROOTS];
-    for (int r = 0; r < RSBLOCKS; r++)
-        for (int i = 0; i < NROOTS; i++) rs_block[r][i] = 0;
-    int nbytes = 0, bindex = COLS, conv_sr = 0;
-    auto put = [&](int c) {                                   // interleave_symbol (:549-556)
-        const int col = bindex / COLS, row = bindex % COLS;
-        if (c) sym[row * ROWS + col] = 1;
-        bindex++;
-    };
-    auto conv = [&](int c, int cnt) {                         // encode_and_interleave (:558-567)
-        while (cnt-- != 0) {
-            conv_sr = ((conv_sr << 1) | ((c >> 7) & 1)) & 0xff;
-            c = (c << 1) & 0xff;
-            put(PT[conv_sr & CPOLYA]);
-            put(1 - PT[conv_sr & CPOLYB]);
-        }
-    };
-    for (int i = 0; i < SYMS; i++) sym[i] = 0;
-    int sr = 0x7f;                                            // sync column (:600-605)
-    for (int i = 0; i < SYNC_LEN; i++) {
-        if (sr & 64) sym[ROWS * i] = 1;
-        sr = ((sr << 1) | PT[sr & SYNC_POLY]) & 0xff;
+    for (int r = 0; r < RSBLOCKS; r++) {
+        int par = 0;
+        for (int i = 0; i < 128; i++) par ^= gf.mul(out[2 * i + r], rs_par[i * NROOTS + lane]);
+        enc[256 + 2 * lane + r] = (uint8_t)(par ^ c_tab.scrambler[256 + 2 * lane + r]);
     }
-    for (int i = 0; i < 256; i++) {                           // :614-655
-        const int c = data[i];
-        const int rsi = nbytes & 1;
-        const int feedback = IO[c ^ rs_block[rsi][0]];
-        if (feedback != A0) {
-            for (int j = 0; j < 15; j++) {
-                const int t = AT[mod255(feedback + c_tab.rs_poly[j])];
-                rs_block[rsi][j + 1] ^= t;
-                rs_block[rsi][31 - j] ^= t;
+    for (int i = lane; i < 256; i += 32) enc[i] = out[i] ^ c_tab.scrambler[i];
+    if (lane < 2) enc[320 + lane] = 0;                        // the six flush bits (:670)
+    __syncwarp();
+    int errors = 0;
+    for (int p = lane; p < SYMS; p += 32) {
+        const int row = p / ROWS, col = p - row * ROWS;
+        int sym = 0;
+        if (col == 0) {
+            sym = c_tab.sync[row] > 0;
+        } else {
+            const int k = col * COLS + row - COLS;            // encoder output number
+            if (k < 2 * NBITS) {
+                const int n = k >> 1, byte = n >> 3;
+                const int two = ((byte ? enc[byte - 1] : 0) << 8) | enc[byte];
+                const int win = (two >> (7 - (n & 7))) & 0x7f;   // input bits n-6 .. n, newest lowest
+                sym = (k & 1) ? 1 - (__popc(win & CPOLYB) & 1) : (__popc(win & CPOLYA) & 1);
             }
-            rs_block[rsi][16] ^= AT[mod255(feedback + c_tab.rs_poly[15])];
         }
-        for (int k = 0; k < 31; k++) rs_block[rsi][k] = rs_block[rsi][k + 1];
-        rs_block[rsi][31] = (feedback != A0) ? AT[feedback] : 0;
-        conv(c ^ c_tab.scrambler[nbytes], 8);
-        nbytes++;
+        errors += (sym != (raw[p] >> 7));
     }
-    for (int i = 0; i < 64; i++) {                            // :662-671
-        const int c = rs_block[nbytes & 1][(nbytes - 256) >> 1];
-        conv(c ^ c_tab.scrambler[nbytes], 8);
-        if (++nbytes == 320) conv(0, 6);
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) errors += __shfl_xor_sync(0xffffffffu, errors, o);
+    return errors;
 }
 
 __global__ void __launch_bounds__(32) k_fec_decode(const int8_t *__restrict__ hist, const int8_t *__restrict__ bits,
                                                    int max_bits, FrameMeta *__restrict__ frames,
                                                    const int *__restrict__ nframes, int max_frames,
-                                                   uint8_t *__restrict__ data_out, long long *__restrict__ cnt_dec)
+                                                   uint8_t *__restrict__ data_out, long long *__restrict__ cnt_dec,
+                                                   const int16_t *__restrict__ mettab, const uint8_t *__restrict__ rs_par)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
     const int slot = blockIdx.x, lane = threadIdx.x;
     if (slot >= min(*nframes, max_frames)) return;
     const FrameMeta m = frames[slot];
+    for (int i = lane; i < 512; i += 32) {
+        S.gf_exp2[i] = c_tab.alpha_to[i < NN ? i : (i < 2 * NN ? i - NN : 0)];
+        (&S.mettab[0][0])[i] = mettab[i];
+    }
+    for (int i = lane; i < 256; i += 32) S.gf_lg[i] = c_tab.index_of[i];
+    const GF gf = {S.gf_exp2, S.gf_lg};
     const int8_t *h = hist + (size_t)m.chan * HIST;
     const int8_t *b = bits + (size_t)m.chan * max_bits;
     // :564-566 dmFECBits[n] = dmFECCorr[n]==1 ? 0xc0 : 0x40
@@ -334,7 +389,7 @@ __global__ void __launch_bounds__(32) k_fec_decode(const int8_t *__restrict__ hi
             const int s0 = S.symbols[2 * bit], s1 = S.symbols[2 * bit + 1];
             int mets[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) mets[i] = c_tab.mettab[(i >> 1) & 1][s0] + c_tab.mettab[i & 1][s1];
+            for (int i = 0; i < 4; i++) mets[i] = S.mettab[(i >> 1) & 1][s0] + S.mettab[i & 1][s1];
             int b1 = mets[sym_e];
             const int b2 = mets[sym_o];
             int m0 = lo + b1;                                  // nmetric[2b] candidates
@@ -376,26 +431,23 @@ __global__ void __launch_bounds__(32) k_fec_decode(const int8_t *__restrict__ hi
     }
     __syncwarp();
     // ---- de-scramble into the two RS code blocks (:762-771)
-    for (int n = lane; n < RSBLOCKS * NN; n += 32) (&S.rs[0][0])[n] = 0;
+    for (int n = lane; n < RSBLOCKS * (NN + 1); n += 32) (&S.rs[0][0])[n] = 0;
     __syncwarp();
     for (int n = lane; n < (NN - RSPAD) * RSBLOCKS; n += 32) {
         const int col = RSPAD + n / RSBLOCKS, row = n % RSBLOCKS;
         S.rs[row][col] = S.vit[n] ^ c_tab.scrambler[n];
     }
     __syncwarp();
-    if (lane < RSBLOCKS) S.rserr[lane] = decode_rs_8(S.rs[lane]);      // :774-777
-    __syncwarp();
-    int rc = (S.rserr[0] == -1 || S.rserr[1] == -1) ? -1 : 0;
+    int rserr[RSBLOCKS];
+    for (int r = 0; r < RSBLOCKS; r++) {                                // :774-777, the warp decodes one word at a time
+        rserr[r] = rs_decode_warp(S.rs[r], S.rsw, gf, lane);
+        __syncwarp();
+    }
+    int rc = (rserr[0] == -1 || rserr[1] == -1) ? -1 : 0;
     if (rc == 0) {
         for (int j = lane; j < 256; j += 32) S.out[j] = S.rs[j % RSBLOCKS][RSPAD + j / RSBLOCKS];   // :783-789
         __syncwarp();
-        if (lane == 0) encode_fec40(S.out, S.reenc);                   // :831-847
-        __syncwarp();
-        int errors = 0;
-        for (int i = lane; i < SYMS; i += 32) errors += (S.reenc[i] != (S.raw[i] >> 7));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) errors += __shfl_xor_sync(0xffffffffu, errors, o);
-        rc = errors;
+        rc = reencode_count_errors(S.out, S.raw, S.enc, rs_par, gf, lane);   // :831-847
         for (int j = lane; j < 256; j += 32) data_out[(size_t)slot * 256 + j] = S.out[j];
         if (lane == 0) atomicAdd((unsigned long long *)&cnt_dec[m.chan], 1ull);
     } else {
@@ -411,11 +463,13 @@ __global__ void __launch_bounds__(32) k_fec_decode(const int8_t *__restrict__ hi
 using namespace jsdr;
 
 struct jsdr_fec_state {
-    int max_frames = 0;
+    int max_frames = 0;                       // frame slots on the device (>= what the caller asked for)
+    int16_t *d_mettab = nullptr;              // [2][256], this bank's copy of the caller's metric table
     int8_t *d_hist[2] = {nullptr, nullptr};   // [nchan][5199]
     int cur = 0;
     fec::FrameMeta *d_frames = nullptr;
     int *d_nframes = nullptr;
+    const uint8_t *d_rs_par = nullptr;        // [128][32] parity map (per device, shared)
     uint8_t *d_data = nullptr;                // [max_frames][256]
     long long *d_cnt = nullptr;               // [2][nchan] cntFEC, cntDec (:567,571)
 };
@@ -425,12 +479,30 @@ extern "C" int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max
     JSDR_REQUIRE(b && mettab && max_frames > 0, JSDR_EINVAL, "bad argument");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
-    fec::Tables t;
-    fec::build_tables(t, mettab);
-    JSDR_CUDA(cudaMemcpyToSymbol(fec::c_tab, &t, sizeof(t)));
-    if (b->fec) return JSDR_OK;                                 // tables refreshed, state kept
+    // generated tables and the parity map: once per device, then read-only
+    static PerDeviceFlag tables_done;
+    static uint8_t *d_rs_par[64] = {nullptr};
+    if (!tables_done.test_and_set(ctx->device)) {
+        fec::Tables t;
+        fec::build_tables(t);
+        JSDR_CUDA(cudaMemcpyToSymbol(fec::c_tab, &t, sizeof(t)));
+        uint8_t par[128][fec::NROOTS];
+        fec::build_rs_parity_map(t, par);
+        JSDR_CUDA(cudaMalloc(&d_rs_par[ctx->device & 63], sizeof(par)));
+        JSDR_CUDA(cudaMemcpy(d_rs_par[ctx->device & 63], par, sizeof(par), cudaMemcpyHostToDevice));
+    }
+    if (b->fec) {                                               // metric table refreshed, state kept: behind this bank's own work
+        JSDR_CUDA(cudaMemcpyAsync(b->fec->d_mettab, mettab, 512 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->aux));
+        JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
+        return JSDR_OK;
+    }
     jsdr_fec_state *f = new jsdr_fec_state();
-    f->max_frames = max_frames;
+    // Every detection of a call is decoded (cntDec must follow cntFEC as in :563-571): a channel
+    // can complete at most one frame per 5200 bits of signal, so nchan * (max_bits/5200 + 2)
+    // slots cover everything but a correlator firing on noise more than twice per frame time.
+    f->max_frames = std::max(max_frames, b->nchan * (b->max_bits / fec::SYMS + 2));
+    f->d_rs_par = d_rs_par[ctx->device & 63];
+    max_frames = f->max_frames;
     const size_t nc = (size_t)b->nchan;
     cudaError_t e = cudaMalloc(&f->d_hist[0], nc * fec::HIST);
     if (e == cudaSuccess) e = cudaMalloc(&f->d_hist[1], nc * fec::HIST);
@@ -438,6 +510,8 @@ extern "C" int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max
     if (e == cudaSuccess) e = cudaMalloc(&f->d_nframes, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&f->d_data, (size_t)max_frames * 256);
     if (e == cudaSuccess) e = cudaMalloc(&f->d_cnt, sizeof(long long) * 2 * nc);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_mettab, 512 * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_mettab, mettab, 512 * sizeof(int16_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("jsdr_bpsk_enable_fec: cudaMalloc: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -473,7 +547,8 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
     if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(fec::k_fec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
-                                                               f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan);
+                                                               f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan,
+                                                               f->d_mettab, f->d_rs_par);
     JSDR_TRY(launched(ctx, "k_fec_decode"));
     dim3 g2((fec::HIST + 255) / 256, nchan);
     fec::k_sync_shift<<<g2, 256, 0, ctx->aux>>>(f->d_hist[f->cur], f->d_hist[f->cur ^ 1], b->d_bits, b->d_nbits, max_bits);
@@ -486,7 +561,7 @@ void jsdr_fec_destroy(jsdr_bpsk *b)
 {
     jsdr_fec_state *f = b->fec;
     if (!f) return;
-    void *ptrs[] = {f->d_hist[0], f->d_hist[1], f->d_frames, f->d_nframes, f->d_data, f->d_cnt};
+    void *ptrs[] = {f->d_hist[0], f->d_hist[1], f->d_frames, f->d_nframes, f->d_data, f->d_cnt, f->d_mettab};
     for (void *p : ptrs) cudaFree(p);
     delete f;
     b->fec = nullptr;
@@ -540,5 +615,29 @@ extern "C" int jsdr_bpsk_read_fec_counters(jsdr_bpsk *b, int64_t *cnt_fec, int64
     JSDR_CUDA(cudaMemcpyAsync(cnt_fec, b->fec->d_cnt, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->aux));
     JSDR_CUDA(cudaMemcpyAsync(cnt_dec, b->fec->d_cnt + nc, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->aux));
     JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
+    return JSDR_OK;
+}
+
+// ---- the tables this library builds for itself, for the reference-pinning tests (host only, no
+// device needed): tests/test_ref_tables.py compares every entry with the literals of
+// FECDecoder.java:40-57,105-181,544-546 and FUNcubeBPSKDemod.java:79-81.
+extern "C" int jsdr_probe_table(int which, int32_t *out, int n)
+{
+    JSDR_REQUIRE(out && n >= 0, JSDR_EINVAL, "null argument");
+    fec::Tables t;
+    fec::build_tables(t);
+    const int sizes[] = {256, 128, 320, 256, 256, 16, fec::SYNC_LEN};
+    JSDR_REQUIRE(which >= 0 && which < 7 && n <= sizes[which], JSDR_EINVAL, "no such table or too many entries");
+    for (int i = 0; i < n; i++) {
+        switch (which) {
+        case 0: out[i] = t.partab[i]; break;
+        case 1: out[i] = t.syms[i]; break;
+        case 2: out[i] = t.scrambler[i]; break;
+        case 3: out[i] = t.alpha_to[i]; break;
+        case 4: out[i] = t.index_of[i]; break;
+        case 5: out[i] = t.rs_poly[i]; break;
+        default: out[i] = t.sync[i]; break;
+        }
+    }
     return JSDR_OK;
 }

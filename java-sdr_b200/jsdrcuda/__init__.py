@@ -115,7 +115,9 @@ _SIGS = {
     "jsdr_fir_set_weights": [_vp, _i, _vp],
     "jsdr_fir_filter_i32": [_vp, _vp, _i, _i64, _vp, _i],
     "jsdr_fir_complex_mod_i32": [_vp, _vp, _vp, _vp, _i64, _i],
-    "jsdr_pump_receive_s16": [_vp, _vp, _vp, _i, _vp, _vp, _i],
+    "jsdr_pump_receive_s16": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i],
+    "jsdr_probe_table": [_i, _vp, _i],
+    "jsdr_probe_taps": [_vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["jsdr_last_error"])
 
@@ -637,6 +639,29 @@ class fir:
 
 
 # ---------------------------------------------------------------------------- the pump
-def pump_receive_s16(f: fft, b: FUNcubeBPSKDemod, raw, nblocks: int, psd, peak_bin=None, mem: int = MEM_HOST):
-    """JavaAudio.run's fan-out (JavaAudio.java:262-304) for [nchan][nblocks*N] s16 IQ."""
-    _ck(lib().jsdr_pump_receive_s16(f.h, b.h, _ptr(raw), nblocks, _ptr(psd), _ptr(peak_bin), mem))
+def pump_receive_s16(f: fft, b: FUNcubeBPSKDemod, raw, nblocks: int, psd, peak_bin=None, mem: int = MEM_HOST,
+                     ic: int = 0, qc: int = 0):
+    """JavaAudio.run's fan-out (JavaAudio.java:262-304) for [nchan][nblocks*N] s16 IQ; ic/qc are
+    the I/Q DC corrections of JavaAudio.java:281-288, seen by both handlers."""
+    _ck(lib().jsdr_pump_receive_s16(f.h, b.h, _ptr(raw), nblocks, ic, qc, _ptr(psd), _ptr(peak_bin), mem))
+
+
+# ---------------------------------------------------------------------------- constant tables
+_TABLE_SIZES = {"Partab": (0, 256), "Syms": (1, 128), "Scrambler": (2, 320), "ALPHA_TO": (3, 256),
+                "INDEX_OF": (4, 256), "RS_poly": (5, 16), "SYNC_VECTOR": (6, 65)}
+
+
+def probe_table(name: str) -> np.ndarray:
+    """A table the library builds for itself (jsdr_probe_table), by its name in the reference
+    (FECDecoder.java:40-181,544-546; FUNcubeBPSKDemod.java:79-81).  No device needed."""
+    which, n = _TABLE_SIZES[name]
+    out = np.empty(n, dtype=np.int32)
+    _ck(lib().jsdr_probe_table(which, _ptr(out), n))
+    return out
+
+
+def probe_taps():
+    """(dsFilter[27], dmFilter[65]) as the kernels use them (FUNcubeBPSKDemod.java:27-77)."""
+    ds, dm = np.empty(27), np.empty(65)
+    _ck(lib().jsdr_probe_taps(_ptr(ds), _ptr(dm)))
+    return ds, dm

@@ -292,6 +292,14 @@ def fec_decode(raw: np.ndarray):
     return rc, out
 
 
+def rs_decode(cw: np.ndarray):
+    """decode_rs_8 (FECDecoder.java:325-519) on one 255-symbol word: (return value, word after)."""
+    cw = np.array(cw, dtype=np.uint8)
+    assert cw.size == 255
+    rc = lib().orc_rs_decode(_p(cw, C.c_uint8))
+    return rc, cw
+
+
 def fec_table_probe(which: int, idx: int) -> int:
     return lib().orc_fec_table_probe(which, idx)
 

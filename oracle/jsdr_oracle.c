@@ -903,6 +903,13 @@ int orc_fec_table_probe(int which, int idx)
     return -1;
 }
 
+static int decode_rs_8(uint8_t *data);
+int orc_rs_decode(uint8_t data[255])
+{
+    fec_tables();
+    return decode_rs_8(data);
+}
+
 void orc_fec_sync_lfsr(uint8_t out[65])
 {
     fec_tables();

@@ -142,6 +142,7 @@ void orc_fec_sync_lfsr(uint8_t out[65]);                    /* :600-605 */
 void orc_fec_encode(const uint8_t data[256], uint8_t sym[5200]); /* :677-688 */
 int  orc_fec_decode(const uint8_t raw[5200], uint8_t out[256]);  /* :703-852 */
 int  orc_fec_table_probe(int which, int idx);                     /* table self-check */
+int  orc_rs_decode(uint8_t data[255]);                            /* decode_rs_8 :325-519, no erasures */
 
 /* ---- CPU baseline drivers (pthreads over channels / blocks) ------------ */
 /* returns the number of threads used */

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in jsdrcuda.h but not exported"
     assert names == jsdrcuda.EXPORTS, "python binding and header disagree on the symbol list"
-    assert lib.jsdr_abi_version() == 1
+    assert lib.jsdr_abi_version() == 2
 
 
 def test_no_cpu_fallback():
