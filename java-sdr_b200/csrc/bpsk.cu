@@ -125,96 +125,147 @@ __device__ __forceinline__ void raw_to_iq(typename RawT<FMT>::type w, int ic, in
 }
 
 // ------------------------------------------------------------------ scouts
-// The tuner phase is data independent but must be replayed add by add to stay
-// bit-exact.  That serial chain (about 25 cycles per step) is all this kernel does:
-// one lane per channel steps the phase through the block and leaves a checkpoint
-// (the phase before the first sample) for every 32-sample chunk.  It runs on the
-// side stream, one block ahead of the data (see bpsk_receive), and costs almost no
-// issue slots, so it hides behind the data kernels.
-// Two reference steps in three dependent additions.  With 0 < inc < pi a wrap cannot follow a
-// wrap, so the pair is one of (no wrap, no wrap), (wrap, none), (none, wrap); which one is
-// PREDICTED from the phase before the pair (p > 2pi-inc, p > 2pi-2inc), off the critical path, and
-// the additions are the reference's own: t1 = p+inc; t2 = t1 + (-2pi | inc); t3 = t2 + (inc | -2pi | 0).
-// The reference's own comparisons (t1 > 2pi, t2 > 2pi) are then evaluated behind the chain and
-// compared with the prediction; a mismatch (p within an ulp or two of a threshold) marks the
-// 32-sample chunk, which is then replayed step by step.  So the result is the reference's sequence
-// by construction, not by an error bound.
-__device__ __forceinline__ double phase_step2(double p, double inc, double th1, double th2, bool &bad)
+// The tuner phase is data independent but must be replayed add by add to stay bit-exact.
+// That serial chain is all this kernel does: it steps every channel's phase through the
+// block and leaves a checkpoint (the phase before the first sample) for every 32-sample
+// chunk.  It runs on the side stream, one block ahead of the data (see bpsk_receive).
+//
+// Two reference steps in three dependent additions and NO comparison on the results.  With
+// 0 < inc < pi a wrap cannot follow a wrap, so a pair of steps is one of (none, none),
+// (wrap, none), (none, wrap), and the additions are the reference's own:
+//   t1 = p + inc;  t2 = t1 + (-2pi | inc);  t3 = t2 + (inc | -2pi | 0).
+// Which pattern applies is decided from the phase BEFORE the pair by two thresholds that are
+// exact, not estimates: rounding is monotone, so {p : fl(p + inc) > 2pi} is an up-set of the
+// doubles and has a largest non-member th1; likewise th2 for fl(fl(p + inc) + inc) > 2pi.  The
+// host finds both by bisection over the bit patterns with the very same additions
+// (scout_thresholds), so `p > th1` IS the reference's `tuPhase > 2pi` of the first step and
+// `p > th2` that of the second — the result is the reference's sequence by construction.
+// Round 1 predicted from approximate thresholds and re-evaluated both comparisons behind the
+// chain (seven more instructions per pair, four of them on the FP64 pipe the chain itself
+// needs): a sub-partition could host one such chain per thread and the bank's replay held 32
+// SMs.  Without them a pair is 3 DADD + 2 DSETP + 6 SEL, so CPT independent chains per
+// thread fit under the latency of one and the same bank needs a third of the SMs.
+struct ScoutChan {
+    double inc, th1, th2, pad;
+};
+
+__device__ __forceinline__ double phase_step2(double p, double inc, double th1, double th2)
 {
     const bool m1 = p > th1, m2 = p > th2;
     const double s2 = m1 ? -kTwoPi : inc;
     const double s3 = m1 ? inc : (m2 ? -kTwoPi : 0.0);
     const double t1 = __dadd_rn(p, inc);
     const double t2 = __dadd_rn(t1, s2);
-    const double t3 = __dadd_rn(t2, s3);
-    const bool w1 = t1 > kTwoPi;                 // :385 as the reference evaluates it
-    const bool w2 = t2 > kTwoPi;                 // the second step's test when the first did not wrap
-    bad |= (w1 != m1) | (!m1 & (w2 != m2));
-    return t3;
+    return __dadd_rn(t2, s3);
 }
 
 constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is scout_threads()
+constexpr int kScoutMaxCpt = 4;
 // Dynamic shared memory a scout CTA asks for (and never uses): more than half an SM's 227 KB, so
 // that two scout CTAs can never share an SM (at 90 KB two did when an SM emptied -- a 1024-channel
 // bank ran its replay in 7.4 ms instead of 6.0); what is left still takes one 67.6 KB CTA of
 // the N = 4096 FFT plan beside it.  JSDR_SCOUT_SMEM_KB overrides it (tuning aid).
 constexpr int kScoutSmem = 116 * 1024;
 
-// CTA size of the phase scout = how many SMs it takes (one CTA each; the streaming data kernel
-// leaves them free when it runs beside it).  The replay runs at full speed with one warp per SM
-// sub-partition (128 threads: 18 cycles per sample) and about a third slower with three (384
-// threads); every user of the bank — the tuner + decimator alone, the pump (where it should finish
-// beside the FFT) and the full chain now that bit timing overlaps the next block — is bound by the
-// replay before it is bound by the SMs it takes, so it gets one warp per sub-partition.
+static int env_int(const char *name, int lo, int hi, int dflt)
+{
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return (v < lo || v > hi) ? dflt : v;
+}
+
+// CTA size and chains per thread of the phase scout = how many SMs it takes (one CTA each; the
+// streaming data kernel leaves them free when it runs beside it).  profiles/r02_scout_sweep.txt
+// has the sweep behind the defaults.  JSDR_SCOUT_THREADS / JSDR_SCOUT_CPT override (tuning aids).
 static int scout_threads(const jsdr_bpsk *b)
 {
     static int forced = -1;
     if (forced < 0) {
-        const char *e = getenv("JSDR_SCOUT_THREADS");          // (tuning aid)
-        forced = e ? atoi(e) : 0;
-        if (forced < 32 || forced > kScoutThreads || (forced & 31)) forced = 0;
+        forced = env_int("JSDR_SCOUT_THREADS", 32, kScoutThreads, 0);
+        if (forced & 31) forced = 0;
     }
-    if (forced) return forced;
     (void)b;
-    return 128;
+    return forced ? forced : 128;
+}
+static int scout_cpt(const jsdr_bpsk *b)
+{
+    static int forced = -1;
+    if (forced < 0) forced = env_int("JSDR_SCOUT_CPT", 1, kScoutMaxCpt, 0);
+    if (forced) return forced;
+    // small banks: one chain per thread keeps the replay's latency (it is the whole cost there)
+    return b->nchan >= 1024 ? 3 : 1;
 }
 
-// One thread per channel; a few hundred channels per CTA, so that a bank's replay occupies a handful of
-// SMs (which the streaming data kernel leaves free) instead of one warp on every SM.
+// Thread t of the grid replays the CPT channels t, t + nthr, t + 2 nthr, ... (consecutive lanes
+// hold consecutive channels, so the checkpoint stores coalesce); the chains of a thread are
+// independent and interleave in the FP64 pipe.
+template <int CPT>
 __global__ void __launch_bounds__(kScoutThreads)
-k_tuner_scout(const double *__restrict__ inc_, const double *__restrict__ phase_in,
+k_tuner_scout(const ScoutChan *__restrict__ par, const double *__restrict__ phase_in,
               double *__restrict__ phase_out, double *__restrict__ ckpt, int nchan, int S)
 {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchan) return;
-    double p = phase_in[ch];
-    const double inc = inc_[ch];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthr = gridDim.x * blockDim.x;
     const int nfull = S >> 5;
-    if (inc > 0.0 && inc < 3.1 && p >= 0.0 && p <= kTwoPi) {
-        const double th1 = __dadd_rn(kTwoPi, -inc), th2 = __dadd_rn(th1, -inc);
-        for (int w = 0; w < nfull; w++) {
-            ckpt[(size_t)w * nchan + ch] = p;
-            const double p0 = p;
-            bool bad = false;
+    double p[CPT], inc[CPT], th1[CPT], th2[CPT];
+    bool live[CPT], fast[CPT];
 #pragma unroll
-            for (int j = 0; j < 16; j++) p = phase_step2(p, inc, th1, th2, bad);
-            if (bad) {
-                p = p0;
-                for (int j = 0; j < 32; j++) p = phase_step(p, inc);
+    for (int k = 0; k < CPT; k++) {
+        const int ch = t + k * nthr;
+        live[k] = ch < nchan;
+        const ScoutChan c = par[live[k] ? ch : 0];
+        p[k] = phase_in[live[k] ? ch : 0];
+        inc[k] = c.inc;
+        th1[k] = c.th1;
+        th2[k] = c.th2;
+        // the pair form covers 0 < inc < 3.1 from a phase inside [0, 2pi]; anything else is replayed
+        // step by step below (a dummy chain keeps this one's slot busy meanwhile)
+        fast[k] = live[k] && inc[k] > 0.0 && inc[k] < 3.1 && p[k] >= 0.0 && p[k] <= kTwoPi;
+    }
+    double q[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        q[k] = fast[k] ? p[k] : 0.0;
+        if (!fast[k]) {
+            inc[k] = 1.0;
+            th1[k] = 5.0;
+            th2[k] = 4.0;
+        }
+    }
+    for (int w = 0; w < nfull; w++) {
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            if (fast[k]) ckpt[(size_t)w * nchan + t + k * nthr] = q[k];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+#pragma unroll
+            for (int k = 0; k < CPT; k++) q[k] = phase_step2(q[k], inc[k], th1[k], th2[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int ch = t + k * nthr;
+        if (!live[k]) continue;
+        double ph;
+        if (fast[k]) {
+            ph = q[k];
+        } else {                                       // increments the pair form does not cover
+            ph = p[k];
+            const double ic = par[ch].inc;
+            for (int w = 0; w < nfull; w++) {
+                ckpt[(size_t)w * nchan + ch] = ph;
+#pragma unroll 4
+                for (int j = 0; j < 32; j++) ph = phase_step(ph, ic);
             }
         }
-    } else {                                           // increments the pair form does not cover
-        for (int w = 0; w < nfull; w++) {
-            ckpt[(size_t)w * nchan + ch] = p;
-#pragma unroll 4
-            for (int j = 0; j < 32; j++) p = phase_step(p, inc);
+        if (S & 31) {
+            const double ic = par[ch].inc;
+            ckpt[(size_t)nfull * nchan + ch] = ph;
+            for (int j = 0; j < (S & 31); j++) ph = phase_step(ph, ic);
         }
+        phase_out[ch] = ph;
     }
-    if (S & 31) {
-        ckpt[(size_t)nfull * nchan + ch] = p;
-        for (int j = 0; j < (S & 31); j++) p = phase_step(p, inc);
-    }
-    phase_out[ch] = p;
 }
 
 // vcoPhase (:511-516) and dmBitPhase (:581-584) are the same for every channel of
@@ -861,28 +912,67 @@ unsigned long long index_step_fixed56(double inc)
     return v ? v : 1ull;
 }
 
+// The exact wrap thresholds of the pair form (see k_tuner_scout): th1 = the largest double p in
+// [0, 2pi] for which the reference's first step does NOT wrap (fl(p + inc) > 2pi is false), th2 the
+// same for the second step of a pair whose first did not wrap.  Rounding is monotone, so both sets
+// are down-sets and bisection over the bit patterns (non-negative doubles order like their
+// integers) with the reference's own additions finds them.  -1 = the step wraps from every phase.
+static void scout_thresholds(double inc, double &th1, double &th2)
+{
+    auto from_bits = [](unsigned long long u) { double x; memcpy(&x, &u, 8); return x; };
+    auto to_bits = [](double x) { unsigned long long u; memcpy(&u, &x, 8); return u; };
+    auto wraps1 = [&](double p) { volatile double t = p + inc; return t > kTwoPi; };
+    auto wraps2 = [&](double p) { volatile double t = p + inc; volatile double u = t + inc; return u > kTwoPi; };
+    auto last_false = [&](auto f) -> double {
+        if (f(0.0)) return -1.0;
+        if (!f(kTwoPi)) return kTwoPi;
+        unsigned long long lo = 0, hi = to_bits(kTwoPi);          // f(lo) false, f(hi) true
+        while (hi - lo > 1) {
+            const unsigned long long mid = lo + (hi - lo) / 2;
+            if (f(from_bits(mid))) hi = mid;
+            else lo = mid;
+        }
+        return from_bits(lo);
+    };
+    th1 = last_false(wraps1);
+    th2 = last_false(wraps2);
+}
+
+static ScoutChan scout_chan(double inc)
+{
+    ScoutChan c;
+    c.inc = inc;
+    c.th1 = c.th2 = c.pad = 0.0;
+    if (inc > 0.0 && inc < 3.1) scout_thresholds(inc, c.th1, c.th2);
+    return c;
+}
+
 // Replay the tuner phase over the next S samples from the committed phase into `P`
 // (side stream).
 int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
 {
     jsdr_ctx *ctx = b->ctx;
     ProfScope prof(ctx, JSDR_K_SCOUT, ctx->side);
-    const int st = scout_threads(b);
-    // The replay is a latency-bound chain that wants a sub-partition's FP64 pipe to itself, and
+    const int st = scout_threads(b), cpt = scout_cpt(b);
+    // The replay is a latency-bound chain that wants its share of a sub-partition's FP64 pipe, and
     // CTAs of a high-priority stream are placed wherever a slot frees up: sixteen of these small
     // CTAs fit in the space one retiring data CTA leaves, and stacked like that they run nine
     // times slower.  A shared-memory request the kernel never touches rules the stacking out:
     // one scout CTA per SM (kScoutSmem, see there).
     static int scout_smem = 0;
-    if (!scout_smem) {
-        const char *e = getenv("JSDR_SCOUT_SMEM_KB");          // (tuning aid)
-        scout_smem = e ? std::max(1, std::min(atoi(e), 200)) * 1024 : kScoutSmem;
-    }
+    if (!scout_smem) scout_smem = env_int("JSDR_SCOUT_SMEM_KB", 1, 200, kScoutSmem / 1024) * 1024;
     static PerDeviceFlag attr_done;
-    if (!attr_done.test_and_set(ctx->device))
-        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
-    k_tuner_scout<<<(b->nchan + st - 1) / st, st, scout_smem, ctx->side>>>(b->d_tu_inc, b->d_tu_phase, P.phase_end, P.ckpt,
-                                                                      b->nchan, S);
+    if (!attr_done.test_and_set(ctx->device)) {
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
+        JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
+    }
+    const int per_cta = st * cpt;
+    const int grid = (b->nchan + per_cta - 1) / per_cta;
+    void (*kern)(const ScoutChan *, const double *, double *, double *, int, int) =
+        cpt == 1 ? k_tuner_scout<1> : cpt == 2 ? k_tuner_scout<2> : cpt == 3 ? k_tuner_scout<3> : k_tuner_scout<4>;
+    kern<<<grid, st, scout_smem, ctx->side>>>(b->d_tu_par, b->d_tu_phase, P.phase_end, P.ckpt, b->nchan, S);
     JSDR_TRY(launched(ctx, "k_tuner_scout"));
     JSDR_CUDA(cudaEventRecord(P.ready, ctx->side));
     P.S = S;
@@ -1338,6 +1428,7 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     ALLOC(b->d_cossin, sizeof(double) * 512);
     ALLOC(b->d_cossin2, sizeof(double2) * 257);
     ALLOC(b->d_tu_inc, sizeof(double) * nc);
+    ALLOC(b->d_tu_par, sizeof(ScoutChan) * nc);
     ALLOC(b->d_tu_dx, sizeof(unsigned long long) * nc);
     ALLOC(b->d_tu_dx56, sizeof(unsigned long long) * nc);
     ALLOC(b->d_tu_phase0, sizeof(double) * nc);
@@ -1385,6 +1476,11 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     if (rc == JSDR_OK) rc = upload(ctx, b->d_taps, taps.data(), sizeof(double) * kMaxDsTaps);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_dmtaps, dmt.data(), sizeof(double) * kDmTaps);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_inc, inc.data(), sizeof(double) * nc);
+    if (rc == JSDR_OK) {
+        std::vector<ScoutChan> par(nchan);
+        for (int c = 0; c < nchan; c++) par[c] = scout_chan(inc[c]);
+        rc = upload(ctx, b->d_tu_par, par.data(), sizeof(ScoutChan) * nc);
+    }
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_dx, dx.data(), sizeof(unsigned long long) * nc);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_tu_dx56, dx56.data(), sizeof(unsigned long long) * nc);
     if (rc == JSDR_OK) rc = upload(ctx, b->d_cossin2, cs2.data(), sizeof(double) * 2 * 257);
@@ -1412,7 +1508,7 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     if (b->ev_ds_read) cudaEventDestroy(b->ev_ds_read);
     for (int i = 0; i < 2; i++)
         if (b->ev_bits_done[i]) cudaEventDestroy(b->ev_bits_done[i]);
-    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
+    void *ptrs[] = {b->d_taps, b->d_dmtaps, b->d_cossin, b->d_tu_inc, b->d_tu_par, b->d_tu_phase0, b->d_tu_dx, b->d_tu_dx56, b->d_cossin2, b->plan[0].ckpt, b->plan[0].phase_end, b->plan[1].ckpt, b->plan[1].phase_end,
                     b->d_ds_hist[0], b->d_ds_hist[1], b->d_ds_out, b->d_vco_state, b->d_vco_ix[0], b->d_vco_ix[1],
                     b->d_bit_roll[0], b->d_bit_roll[1], b->d_dm_hist[0], b->d_dm_hist[1], b->d_dm_buf[0], b->d_dm_buf[1], b->d_ts, b->d_bits,
                     b->d_bit_at, b->d_nbits, b->d_in, b->d_at_work[0], b->d_at_work[1], b->d_at_rev[0], b->d_at_rev[1], b->d_at_state};
@@ -1483,6 +1579,8 @@ extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
     JSDR_TRY(upload(b->ctx, b->d_tu_dx + chan, &dx, sizeof(dx)));
     unsigned long long dx56 = index_step_fixed56(inc);
     JSDR_TRY(upload(b->ctx, b->d_tu_dx56 + chan, &dx56, sizeof(dx56)));
+    const ScoutChan sc = scout_chan(inc);
+    JSDR_TRY(upload(b->ctx, b->d_tu_par + chan, &sc, sizeof(sc)));
     return upload(b->ctx, b->d_tu_inc + chan, &inc, sizeof(double));
 }
 

@@ -41,6 +41,7 @@ struct AutoTuneState {
     int centreBin, pad;
 };
 
+struct ScoutChan;                    // bpsk.cu
 constexpr int kMaxDsTaps = 128;
 constexpr int kDmTaps = 65;          // MATCHED_FILTER_SIZE
 
@@ -63,6 +64,7 @@ struct jsdr_bpsk {
     double2 *d_cossin2 = nullptr;    // (cos, sin) pairs, plus entry 256 = (1, 1) for the mixer bypass
 
     double *d_tu_inc = nullptr;      // [nchan] tuPhaseInc
+    jsdr::bpsk::ScoutChan *d_tu_par = nullptr;   // [nchan] increment and exact wrap thresholds (phase scout)
     unsigned long long *d_tu_dx = nullptr;   // [nchan] table-index step per sample, 8.48 fixed point
     unsigned long long *d_tu_dx56 = nullptr; // [nchan] the same in 8.56 fixed point (streaming kernel)
     int precision = 0;               // JSDR_PREC_F64 (exact) or JSDR_PREC_F32 (decimator in binary32)

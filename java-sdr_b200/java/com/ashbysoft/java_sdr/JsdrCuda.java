@@ -2,7 +2,8 @@
 //
 // NOT COMPILED IN THIS REPOSITORY'S BUILD ENVIRONMENT: the image has no JDK (see
 // DESIGN.md).  It is the reference-side binding a java-sdr maintainer adds next to
-// fft.java / FUNcubeBPSKDemod.java; every downcall below is one entry point of
+// fft.java / FUNcubeBPSKDemod.java (with CudaFft.java, CudaFUNcubeBPSKDemod.java and the three
+// insert-only patches under ../../../patches/); every downcall below is one entry point of
 // include/jsdrcuda.h, with the same argument order.  The Python mirror of these
 // classes (java-sdr_b200/jsdrcuda) is what the tests drive through the same ABI.
 package com.ashbysoft.java_sdr;
@@ -57,7 +58,12 @@ public final class JsdrCuda {
 	static final MethodHandle BPSK_READ_BITS = h("jsdr_bpsk_read_bits",
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
 	static final MethodHandle PUMP_RECEIVE_S16 = h("jsdr_pump_receive_s16",
-		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle BPSK_LAST_COUNTS = h("jsdr_bpsk_last_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	static final MethodHandle BPSK_READ_DS = h("jsdr_bpsk_read_ds", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle BPSK_READ_DM = h("jsdr_bpsk_read_dm", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle BPSK_READ_FEC_COUNTERS = h("jsdr_bpsk_read_fec_counters",
+		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 	static final MethodHandle BPSK_READ_DS_ASYNC = h("jsdr_bpsk_read_ds_async",
 		FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
 	static final MethodHandle BPSK_READ_COUNTERS = h("jsdr_bpsk_read_counters",
@@ -99,10 +105,32 @@ public final class JsdrCuda {
 		}
 	}
 
-	/** One context per JVM / GPU; pinned rings are allocated from it. */
+	// ---- the context every patched handler shares (one per JVM / GPU), created on first use.
+	// null when libjsdrcuda.so or a CUDA device is missing: the handlers then keep running the
+	// reference's own Java arithmetic (there is no CPU fallback inside the library).
+	private static Context sharedCtx;
+	private static boolean sharedTried;
+
+	static synchronized Context shared(ILogger logger) {
+		if (!sharedTried) {
+			sharedTried = true;
+			try {
+				sharedCtx = new Context(Integer.getInteger("jsdrcuda.device", 0));
+			} catch (Throwable t) {
+				logger.statusMsg("libjsdrcuda.so not in use: " + t);
+			}
+		}
+		return sharedCtx;
+	}
+
+	/** One context per JVM / GPU; pinned rings are allocated from it.  The header's threading
+	 *  rule (a context and its handles are driven by one thread at a time) is kept by taking
+	 *  `lock` around every native call: CudaFft and CudaFUNcubeBPSKDemod do, and nothing else
+	 *  calls into the library. */
 	public static final class Context implements AutoCloseable {
 		final MemorySegment handle;
 		final Arena arena = Arena.ofShared();
+		final Object lock = new Object();
 
 		public Context(int device) throws Throwable {
 			MemorySegment out = arena.allocate(ADDRESS);
@@ -117,6 +145,12 @@ public final class JsdrCuda {
 			String err = check((int) HOST_ALLOC.invokeExact(handle, bytes, out));
 			if (err != null) throw new OutOfMemoryError(err);
 			return out.get(ADDRESS, 0).reinterpret(bytes);
+		}
+
+		/** Returns a pinned() segment to the library (no-op for null).  Caller holds `lock`. */
+		void free(MemorySegment p) {
+			if (p == null) return;
+			try { int rc = (int) HOST_FREE.invokeExact(handle, p); } catch (Throwable t) { }
 		}
 
 		@Override
