@@ -35,6 +35,8 @@ extern "C" int jsdr_device_count(int *count)
     return JSDR_OK;
 }
 
+static int ctx_init(jsdr_ctx *ctx);
+
 extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
 {
     JSDR_REQUIRE(out, JSDR_EINVAL, "null argument");
@@ -58,6 +60,17 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     jsdr_ctx *ctx = new jsdr_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    const int rc = ctx_init(ctx);
+    if (rc != JSDR_OK) {                              // half-built: release what exists (destroy skips null handles)
+        jsdr_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return JSDR_OK;
+}
+
+static int ctx_init(jsdr_ctx *ctx)
+{
     if (const char *e = getenv("JSDR_L2_PREFETCH")) ctx->l2_prefetch = std::max(0, std::min(atoi(e), 8));   // 0: off, n: n x resident CTAs ahead
     {   // three priorities: the side stream carries the serial, data-independent phase replay and
         // goes first, so that its few CTAs are placed as soon as a slot frees up instead of queueing
@@ -83,7 +96,6 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux_join, cudaEventDisableTiming));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     JSDR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    *out = ctx;
     return JSDR_OK;
 }
 
@@ -91,30 +103,24 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
 {
     if (!ctx) return JSDR_OK;
     ctx->bind();
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->side);
-    cudaStreamSynchronize(ctx->side2);
-    cudaEventDestroy(ctx->ev_t0);
-    cudaEventDestroy(ctx->ev_t1);
-    cudaEventDestroy(ctx->ev_aux_fork);
-    cudaEventDestroy(ctx->ev_aux_join);
-    cudaEventDestroy(ctx->ev_fork);
-    cudaEventDestroy(ctx->ev_join);
+    cudaStream_t *streams[] = {&ctx->stream, &ctx->side, &ctx->side2, &ctx->aux, &ctx->copy_in, &ctx->copy_out};
+    for (cudaStream_t *s : streams)
+        if (*s) cudaStreamSynchronize(*s);            // events below may still be pending on any of them
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_aux_fork, ctx->ev_aux_join, ctx->ev_fork, ctx->ev_join};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
     for (auto *v : {&ctx->spans, &ctx->free_spans})
         for (jsdr_prof_span &sp : *v) {
             cudaEventDestroy(sp.a);
             cudaEventDestroy(sp.b);
         }
     for (int i = 0; i < 16; i++) {
-        cudaEventDestroy(ctx->ev_chunk_in[i]);
-        cudaEventDestroy(ctx->ev_chunk_done[i]);
+        if (ctx->ev_chunk_in[i]) cudaEventDestroy(ctx->ev_chunk_in[i]);
+        if (ctx->ev_chunk_done[i]) cudaEventDestroy(ctx->ev_chunk_done[i]);
     }
-    cudaStreamDestroy(ctx->aux);
-    cudaStreamDestroy(ctx->copy_in);
-    cudaStreamDestroy(ctx->copy_out);
-    cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->side);
-    cudaStreamDestroy(ctx->side2);
+    for (cudaStream_t *s : streams)
+        if (*s) cudaStreamDestroy(*s);
+    cudaGetLastError();
     delete ctx;
     return JSDR_OK;
 }
@@ -150,21 +156,27 @@ extern "C" int jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, 
 {
     JSDR_REQUIRE(ctx && ms && count && nkinds >= JSDR_K_COUNT, JSDR_EINVAL, "need room for JSDR_K_COUNT kinds");
     JSDR_TRY(ctx->bind());
-    JSDR_CUDA(cudaStreamSynchronize(ctx->side));
-    JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    JSDR_TRY(jsdr_ctx_sync(ctx));                   // spans are recorded on every compute stream (bit timing: aux)
     for (int k = 0; k < nkinds; k++) {
         ms[k] = 0.0;
         count[k] = 0;
     }
+    int rc = JSDR_OK;
     for (jsdr_prof_span &sp : ctx->spans) {
         float t = 0.f;
-        JSDR_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
-        ms[sp.kind] += t;
-        count[sp.kind]++;
-        ctx->free_spans.push_back(sp);
+        const cudaError_t e = cudaEventElapsedTime(&t, sp.a, sp.b);
+        if (e == cudaSuccess) {
+            ms[sp.kind] += t;
+            count[sp.kind]++;
+        } else if (rc == JSDR_OK) {
+            set_error("jsdr_ctx_profile_read: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            rc = JSDR_ECUDA;
+        }
+        ctx->free_spans.push_back(sp);                // every span moves exactly once, error or not
     }
     ctx->spans.clear();
-    return JSDR_OK;
+    return rc;
 }
 
 extern "C" int jsdr_host_alloc(jsdr_ctx *ctx, size_t bytes, void **out)

@@ -185,16 +185,25 @@ static int scout_threads(const jsdr_bpsk *b)
         forced = env_int("JSDR_SCOUT_THREADS", 32, kScoutThreads, 0);
         if (forced & 31) forced = 0;
     }
-    (void)b;
-    return forced ? forced : 128;
+    if (forced) return forced;
+    // One warp per SM sub-partition (128 threads) is the fastest replay: 5.2 ms per 2^19-sample
+    // block whatever the bank size, on nchan/128 SMs.  That is what a bank on its own wants (tuner
+    // + decimator alone is bound by the replay, BASELINE config 4).  In the pump the data kernels
+    // take 8 ms per block, so the replay may take 6.4 ms on half the SMs (two warps per
+    // sub-partition): the FFT beside it gets 16 SMs back (4.63 -> 4.28 ms, step 8.29 -> 8.23 ms).
+    return (b->in_pump && b->nchan >= 2048) ? 256 : 128;
 }
 static int scout_cpt(const jsdr_bpsk *b)
 {
     static int forced = -1;
     if (forced < 0) forced = env_int("JSDR_SCOUT_CPT", 1, kScoutMaxCpt, 0);
     if (forced) return forced;
-    // small banks: one chain per thread keeps the replay's latency (it is the whole cost there)
-    return b->nchan >= 1024 ? 3 : 1;
+    // One chain per thread.  Several independent chains per thread would interleave in the FP64 pipe
+    // in principle, but ptxas schedules the unrolled chains one after the other (cuobjdump: 48
+    // dependent DADDs of chain 0, then 48 of chain 1), so CPT = 2..4 measured 2.8-4.5x SLOWER
+    // (profiles/r02_scout_sweep.txt); more warps per CTA is the form that works.
+    (void)b;
+    return 1;
 }
 
 // Thread t of the grid replays the CPT channels t, t + nthr, t + 2 nthr, ... (consecutive lanes

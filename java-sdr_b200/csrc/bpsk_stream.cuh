@@ -416,7 +416,15 @@ __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
                     const int c = min(max(s_hi >> 5, 0), p.nchunks - 1);
                     const double ck = p.ckpt[(size_t)c * p.nchan + ch];
                     x_top = phase_to_x56(ck) + (unsigned long long)((long long)(s_hi - (c << 5) + 1)) * dx;
-                    bad_anchor = !(ck >= 0.0);
+                    // The index is extrapolated backwards from this anchor over the next kReanchor
+                    // periods.  Samples whose phase is <= 0 take the mixer bypass (:395) instead of a
+                    // table entry; that only happens while the phase climbs from below zero after a
+                    // retune from a negative frequency, so the whole anchor window is clear of it as
+                    // soon as the checkpoint of its OLDEST chunk is non-negative (inc > 0: the phase
+                    // only grows from there).  Otherwise the lane replays exactly.
+                    const int c_lo = min(max((s_hi - kReanchor * DD + 1) >> 5, 0), p.nchunks - 1);
+                    const double ck_lo = p.ckpt[(size_t)c_lo * p.nchan + ch];
+                    bad_anchor = !(ck >= 0.0) || !(ck_lo >= 0.0);
                 }
                 // Sample j of the period sits j steps below the top: hi32(x_top - j*dx) lies in
                 // [X - j, X] for X = hi32(x_top) - j*hi32(dx) (the low words can borrow at most j), so
