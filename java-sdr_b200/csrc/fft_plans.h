@@ -14,5 +14,5 @@
     X(16384, 512, 1, 32, 32, 16, 1)  \
     X(4410, 224, 1, 10, 21, 21, 1)   \
     X(4800, 320, 1, 20, 16, 15, 1)   \
-    X(9600, 480, 1, 20, 20, 24, 1)   \
+    X(9600, 320, 1, 32, 20, 15, 1)   \
     X(19200, 640, 1, 16, 16, 15, 5)
