@@ -156,7 +156,10 @@ class ClockSampler:
 
 
 def cpu_pipeline(a, seconds, nthreads):
-    """The oracle port of the same pipeline on a bounded sample; returns the cpu_baseline object."""
+    """The oracle port of the same pipeline on a bounded sample; returns the cpu_baseline object.
+    Timed with the FFT plan cached per thread and modulo-free loops (oracle fft mode 1): that is
+    MORE favourable to the CPU than the reference's own code, which builds a new FloatFFT_1D for
+    every block (fft.java:194); the plan-per-block form is timed on a short sample beside it."""
     import oracle as O
     from oracle import siggen
     taps = siggen.lowpass_taps(a.taps, 4800.0, RATE)
@@ -169,16 +172,25 @@ def cpu_pipeline(a, seconds, nthreads):
         t0 = time.perf_counter()
         _, _, used = O.baseline_pipeline_s16(raw, nch, nblk, a.fft_n, RATE, tun, taps, nthreads)
         return time.perf_counter() - t0, used
+    O.baseline_set_fft_mode(1)
     dt, used = run(probe_ch)
     per_ch = dt / probe_ch
     nch = int(max(probe_ch, min(seconds / max(per_ch, 1e-9), 200000)))
     nch = (nch // max(nthreads, 1)) * max(nthreads, 1)
     dt, used = run(nch)
     v = nch * nblk * a.fft_n / dt / 1e6
+    O.baseline_set_fft_mode(0)
+    nch0 = max(probe_ch, nch // 8)
+    dt0, _ = run(nch0)
+    v0 = nch0 * nblk * a.fft_n / dt0 / 1e6
     return {"value": round(v, 3), "unit": "Msamples/s", "cores": used, "kind": "port",
             "sample": f"{nch} channels x {nblk} block x N={a.fft_n} of the same pipeline "
-                      f"(s16->float, float FFT with per-block plan + PSD, tuner + {a.taps}-tap decimator), "
-                      f"{dt:.1f} s on {used} threads; C port of the Java arithmetic (no JVM in this image)"}
+                      f"(s16->float, float FFT + PSD, tuner + {a.taps}-tap decimator), "
+                      f"{dt:.1f} s on {used} threads; C port of the Java arithmetic (no JVM in this image), "
+                      f"FFT plan cached per thread",
+            "plan_per_block": {"value": round(v0, 3), "unit": "Msamples/s",
+                               "note": "the same with the FFT plan and twiddle table rebuilt for every block, "
+                                       "as fft.java:194 does (new FloatFFT_1D per receive)"}}
 
 
 def run_reference(a):
@@ -328,6 +340,71 @@ def main():
     chain_ms = ctx.timer_stop_ms() / 3
     bank_c.close()
 
+    # ---- the same step at the reference's own block lengths, N = rate/10 (fft.java:67,
+    # JavaAudio.java:59): 19200 at 192 kS/s (D = 20) and 9600 at 96 kS/s (D = 10), same resident batch
+    # (as many whole blocks per channel as fit in the 2^31-sample buffer)
+    def rate10_variant(vrate):
+        vn = vrate // 10
+        vblk = S // vn
+        vS = vblk * vn
+        vadsc = J.AudioDescriptor(vrate)
+        vf = J.fft(ctx, None, vadsc, max_batch=nchan * vblk, n=vn)
+        vbank = J.FUNcubeBPSKDemod(ctx, None, vadsc, tuning=tuning * (vrate / RATE), max_block=vS, stages=1)
+        vtaps = a.taps if vrate == RATE else 27          # 96 kS/s: the reference's own 27-tap low-pass (:27-55)
+        if vtaps != 27:
+            vbank.set_ds_filter(J.design_lowpass(vtaps, 4800.0, vrate))
+        vbank.set_precision(J.PREC_F32 if a.precision == "f32" else J.PREC_F64)
+        vstep = lambda: J.pump_receive_s16(vf, vbank, d_raw, vblk, d_psd, d_peak, mem=J.MEM_DEVICE)
+        for _ in range(3):
+            vstep()
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_read()
+        ctx.timer_start()
+        reps = max(3, a.steps // 4)
+        for _ in range(reps):
+            vstep()
+        vms = ctx.timer_stop_ms() / reps
+        vk = ctx.profile_read()
+        ctx.profile(False)
+        vf.close()
+        vbank.close()
+        return {"n": vn, "rate": vrate, "blocks": vblk, "samples": nchan * vS, "ms": vms, "taps": vtaps,
+                "fft_ms": vk["fft"][0] / max(vk["fft"][1], 1), "mix_ms": vk["mixdecim"][0] / max(vk["mixdecim"][1], 1)}
+    v192 = rate10_variant(192000)
+    v96 = rate10_variant(96000)
+
+    # ---- latency at the reference's operating point: ONE stream, one block of rate/10 samples
+    # per 100 ms (JavaAudio.java:231-233), the fft handler and two FUNcube tuners on it
+    # (jsdr.java:476,479), host buffers, results back in host memory — per call, through the C ABI
+    lat = None
+    if rank == 0:
+        ln = RATE // 10
+        f_l = J.fft(ctx, None, adsc, max_batch=1, n=ln)
+        bank_l = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0, 14000.0], max_block=ln, stages=3)
+        blk = synth_tile(1, ln, 5)[0]
+        t_fft, t_bpsk = [], []
+        for i in range(230):
+            t0 = time.perf_counter()
+            f_l.receive_raw(blk)
+            t1 = time.perf_counter()
+            bank_l.receive_raw(blk, shared=True)
+            bank_l.read_bits()
+            t2 = time.perf_counter()
+            if i >= 30:
+                t_fft.append((t1 - t0) * 1e6)
+                t_bpsk.append((t2 - t1) * 1e6)
+        f_l.close()
+        bank_l.close()
+        pct = lambda v, q: round(float(np.percentile(v, q)), 1)
+        lat = {"unit": "us", "block": f"N={ln} s16 IQ (one 100 ms block at 192 kS/s), MEM_HOST, 200 calls after 30 warm-up",
+               "fft_receive_s16": {"p50": pct(t_fft, 50), "p99": pct(t_fft, 99)},
+               "bpsk_receive_s16_2_tuners_to_bits": {"p50": pct(t_bpsk, 50), "p99": pct(t_bpsk, 99)},
+               "budget_us": 100000,
+               "note": "jsdr_fft_receive_s16 (H2D, FFT+PSD, D2H) and jsdr_bpsk_receive_s16 + jsdr_bpsk_read_bits "
+                       "(shared stream, tuner .. bit decisions) as the patched java-sdr handlers call them; "
+                       "includes the ctypes call overhead"}
+
     # ---- end to end through the C ABI with host (pinned) buffers
     e_ch = min(a.e2e_channels, nchan)
     e_batch = e_ch * nblk
@@ -355,6 +432,22 @@ def main():
     e2e_samples = e_ch * S
     h2d = h_raw.nbytes
     d2h = h_psd.nbytes + h_pk.nbytes + h_ds.nbytes
+    # the same with waterfall.java's paintLine on the device: pixel rows come back instead of the PSD
+    WF_W = 1024
+    h_pix = ctx.host_alloc((e_batch, WF_W), np.int32)
+    h_peak = ctx.host_alloc((e_batch, 2), np.float32)
+    def e2e_wf_step():
+        J.pump_waterfall_s16(f_e, bank_e, h_raw, nblk, WF_W, h_pix, h_peak, h_pk, mem=J.MEM_HOST)
+        bank_e.read_ds_async(h_ds)
+    for _ in range(2):
+        e2e_wf_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_wf_step()
+    ctx.sync()
+    e2e_wf_s = (time.perf_counter() - t0) / a.steps
+    d2h_wf = h_pix.nbytes + h_peak.nbytes + h_pk.nbytes + h_ds.nbytes
 
     # ---- reduce over ranks: max time, summed work
     t_step = ms / a.steps
@@ -362,8 +455,10 @@ def main():
     if dist is not None:
         import torch
         dev = torch.device("cuda", local)
-    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms), launches = sharding.reduce_timing(
-        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms], launches)
+    (t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms, v192["ms"], v192["fft_ms"], v96["ms"],
+     v96["fft_ms"], e2e_wf_s), launches = sharding.reduce_timing(
+        dist, dev, [t_step, fft_ms, mix_ms, e2e_s, other_ms, scout_ms, chain_ms, mixonly_ms, v192["ms"], v192["fft_ms"],
+                    v96["ms"], v96["fft_ms"], e2e_wf_s], launches)
     launches = int(launches)
 
     if rank == 0:
@@ -406,8 +501,8 @@ def main():
                          "fft_kernel_alone": {"ms_per_launch": round(fft_alone_ms, 4),
                                               "achieved": round(fft_bytes / (fft_alone_ms * 1e-3) / 1e9, 1),
                                               "frac": round(fft_bytes / (fft_alone_ms * 1e-3) / 1e9 / peak, 4),
-                                              "note": "same launch outside the pipeline (rank 0): in the step it shares 32 SMs "
-                                                      "with the phase scout of the next block"},
+                                              "note": "same launch outside the pipeline (rank 0): in the step the phase scout "
+                                                      "of the next block holds 16 SMs beside it"},
                          "other_kernels": kernels[1:] + [{"kernel": "k_tuner_scout (exact tuner phase replay, side stream, overlapped)",
                                                           "ms_per_launch": round(scout_ms, 4)}],
                          "pipeline": {"algorithmic_bytes_per_step_fused": step_bytes,
@@ -422,6 +517,20 @@ def main():
                                                   "frac_of_hbm_peak": round((samples * 4 + nout * 16) / (mixonly_ms * 1e-3) / 1e9 / peak, 4),
                                                   "note": "BASELINE config 4 alone: NCO mix + %d-tap FIR decimate x%d (%s), "
                                                           "4 + 16/D algorithmic bytes per sample" % (a.taps, D, a.precision)},
+                         **{"fft_n%d" % v["n"]: {
+                             "value": round(world * v["samples"] / (v["ms"] * 1e-3) / 1e6, 1), "unit": "Msamples/s",
+                             "ms_per_step": round(v["ms"], 4),
+                             "fft_ms_per_launch": round(v["fft_ms"], 4),
+                             "fft_frac_of_hbm_peak": round((v["samples"] * 8 + nchan * v["blocks"] * 8) / (v["fft_ms"] * 1e-3) / 1e9 / peak, 4),
+                             "pipeline_frac_of_hbm_peak": round((v["samples"] * 8 + nchan * (v["blocks"] * v["n"] // (v["rate"] // 9600)) * 16)
+                                                                / (v["ms"] * 1e-3) / 1e9 / peak, 4),
+                             "note": "the same step at the reference's own block length N = rate/10 (fft.java:67): %d ch x %d blk x "
+                                     "N=%d @ %d kS/s, %d-tap decimate x%d" % (nchan, v["blocks"], v["n"], v["rate"] // 1000, v["taps"], v["rate"] // 9600)}
+                            for v in (v192, v96)},
+                         "e2e_waterfall_rows": {"value": round(world * e2e_samples / e2e_wf_s / 1e6, 1), "unit": "Msamples/s",
+                                                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_wf),
+                                                "note": "e2e with waterfall.java's paintLine on the device (jsdr_pump_waterfall_s16, "
+                                                        "%d-pixel rows): pixel rows + peak values + decimated rows return instead of the PSD" % WF_W},
                          "funcube_chain_to_bits": {"value": round(world * samples / (chain_ms * 1e-3) / 1e6, 1),
                                                    "unit": "Msamples/s", "ms_per_step": round(chain_ms, 4),
                                                    "note": "tuner + 27-tap decimator + 65-tap matched filter + bit timing "
@@ -429,6 +538,7 @@ def main():
             "e2e": {"value": round(world * e2e_samples / e2e_s / 1e6, 1), "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "sample": f"{e_ch} channels x {nblk} blocks per rank through jsdr_pump_receive_s16 + jsdr_bpsk_read_ds with pinned host buffers"},
+            "latency": lat,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -72,7 +72,8 @@ int         jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count);
  * the summed milliseconds and launch counts per kind since the last read
  * (ms/count hold JSDR_K_COUNT entries).  bench.py's roofline numbers come from here. */
 enum { JSDR_K_FFT = 0, JSDR_K_MIXDECIM = 1, JSDR_K_MATCHED = 2, JSDR_K_TIMING = 3, JSDR_K_SCOUT = 4,
-       JSDR_K_OTHER = 5, JSDR_K_COUNT = 6 };
+       JSDR_K_OTHER = 5, JSDR_K_DEMOD = 6, JSDR_K_FIR = 7, JSDR_K_DETECT = 8, JSDR_K_WATERFALL = 9,
+       JSDR_K_SYNC = 10, JSDR_K_FEC = 11, JSDR_K_COUNT = 12 };
 int         jsdr_ctx_profile(jsdr_ctx *ctx, int enable);
 int         jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, int nkinds);
 
@@ -271,6 +272,14 @@ int jsdr_probe_taps(double ds27[27], double dm65[65]);
  */
 int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
                           int ic, int qc, float *psd, int32_t *peak_bin, int mem);
+/* The same fan-out with waterfall.java's paintLine (waterfall.java:90-107, as in
+ * jsdr_waterfall_rows) chained behind every block's PSD on the device: what comes back is the
+ * ARGB pixel row a waterfall draws, pixels[nchan*nblocks][width], and the two published maxima
+ * of fft.java:223-224, peak[nchan*nblocks][2] = {peak Hz, peak dB} — 4*width + 8 bytes per
+ * block instead of 4*(n+2).  For consumers that only paint (waterfall.java:28-47). */
+int jsdr_pump_waterfall_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
+                            int ic, int qc, int width, uint32_t peak_rgb, int32_t *pixels,
+                            float *peak, int32_t *peak_bin, int mem);
 
 #ifdef __cplusplus
 }

@@ -1737,10 +1737,42 @@ int pump_fft(void *user, const void *d_in)
 
 // JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: each channel's
 // blocks go to the fft handler and to the tuner bank.
+namespace {
+struct PumpPixels {          // jsdr_pump_waterfall_s16: pixel rows and the two trailing floats instead of the PSD
+    int width;
+    uint32_t rgb;
+    int32_t *pixels;         // [batch][width]
+    float *peak;             // [batch][2]: psd[N] (peak Hz), psd[N+1] (peak dB)
+};
+int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc, float *psd,
+                 int32_t *peak_bin, int mem, const PumpPixels *px);
+}  // namespace
+
 extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
                                      int ic, int qc, float *psd, int32_t *peak_bin, int mem)
 {
-    JSDR_REQUIRE(f && b && raw && psd, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(psd, JSDR_EINVAL, "null argument");
+    return pump_receive(f, b, raw, nblocks, ic, qc, psd, peak_bin, mem, nullptr);
+}
+
+// The same fan-out with waterfall.java's paintLine (:90-107) chained behind every block's PSD on
+// the device: what returns is the pixel row a waterfall draws and the two published maxima
+// (fft.java:223-224), 4*width + 8 bytes per block instead of 4*(N+2).
+extern "C" int jsdr_pump_waterfall_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc,
+                                       int width, uint32_t peak_rgb, int32_t *pixels, float *peak, int32_t *peak_bin,
+                                       int mem)
+{
+    JSDR_REQUIRE(f && pixels && peak, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(width > 0 && width <= f->n, JSDR_EINVAL, "need 0 < width <= n");
+    PumpPixels px = {width, peak_rgb, pixels, peak};
+    return pump_receive(f, b, raw, nblocks, ic, qc, nullptr, peak_bin, mem, &px);
+}
+
+namespace {
+int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc, float *psd,
+                 int32_t *peak_bin, int mem, const PumpPixels *px)
+{
+    JSDR_REQUIRE(f && b && raw, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(f->ctx == b->ctx, JSDR_EINVAL, "handlers belong to different contexts");
     JSDR_REQUIRE(nblocks > 0, JSDR_EINVAL, "nblocks must be positive");
     const long long S = (long long)nblocks * f->n;
@@ -1755,7 +1787,7 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     job.ic = ic;                                   // JavaAudio.java:281-288: both handlers see the corrected samples
     job.qc = qc;
     const size_t psd_elems = (size_t)batch * (f->n + 2);
-    if (mem == JSDR_MEM_DEVICE) {
+    if (mem == JSDR_MEM_DEVICE && !px) {
         job.d_psd = psd;
         job.d_peak = peak_bin;
         b->in_pump = 1;
@@ -1771,6 +1803,19 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
         f->out_cap = psd_elems * sizeof(float);
     }
     if (!f->d_peak) JSDR_CUDA(cudaMalloc(&f->d_peak, sizeof(int32_t) * (size_t)f->max_batch));
+    const int N2 = f->n + 2;
+    if (mem == JSDR_MEM_DEVICE) {                      // pixel rows from a resident batch: FFT, paintLine, tuner bank
+        job.d_psd = f->d_out;
+        job.d_peak = peak_bin ? peak_bin : f->d_peak;
+        JSDR_TRY(fft::launch(f, raw, fft::IN_S16, (int)batch, job.d_psd, job.d_peak, fft::OUT_PSD, ic, qc, ctx->stream));
+        JSDR_TRY(jsdr_launch_waterfall(ctx, f->d_out, f->n, (int)batch, px->width, px->rgb, px->pixels, ctx->stream));
+        JSDR_CUDA(cudaMemcpy2DAsync(px->peak, 2 * sizeof(float), f->d_out + f->n, N2 * sizeof(float), 2 * sizeof(float),
+                                    (size_t)batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        b->in_pump = 1;
+        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, ic, qc, mem);
+        b->in_pump = 0;
+        return rc;
+    }
     const size_t in_bytes = (size_t)b->nchan * (size_t)S * 4;
     if (b->in_cap < in_bytes) {
         cudaFree(b->d_in);
@@ -1779,9 +1824,19 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
         JSDR_CUDA(cudaMalloc(&b->d_in, in_bytes));
         b->in_cap = in_bytes;
     }
+    if (px) {
+        const size_t pix_bytes = (size_t)batch * px->width * sizeof(int32_t);
+        if (f->pix_cap < pix_bytes) {
+            cudaFree(f->d_pix);
+            f->d_pix = nullptr;
+            f->pix_cap = 0;
+            JSDR_CUDA(cudaMalloc(&f->d_pix, pix_bytes));
+            f->pix_cap = pix_bytes;
+        }
+    }
     // Host path, pipelined over channel chunks: PCIe is full duplex, so the upload of chunk
     // c+1 (copy_in stream) runs beside the FFT of chunk c (main stream) and the download of
-    // the PSD of chunk c-1 (copy_out stream).  The tuner bank runs once the whole batch is in.
+    // the results of chunk c-1 (copy_out stream).  The tuner bank runs once the whole batch is in.
     const int nchunk = std::min(16, std::max(1, b->nchan / 8));
     JSDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));            // staging buffers are free again
     JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
@@ -1794,12 +1849,22 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
                                   cudaMemcpyHostToDevice, ctx->copy_in));
         JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_in[c], ctx->copy_in));
         JSDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk_in[c], 0));
-        JSDR_TRY(fft::launch(f, (const char *)b->d_in + in_off, fft::IN_S16, (int)nblk, f->d_out + blk0 * (f->n + 2),
+        JSDR_TRY(fft::launch(f, (const char *)b->d_in + in_off, fft::IN_S16, (int)nblk, f->d_out + blk0 * N2,
                              f->d_peak + blk0, fft::OUT_PSD, ic, qc, ctx->stream));
+        if (px)
+            JSDR_TRY(jsdr_launch_waterfall(ctx, f->d_out + blk0 * N2, f->n, (int)nblk, px->width, px->rgb,
+                                           f->d_pix + blk0 * px->width, ctx->stream));
         JSDR_CUDA(cudaEventRecord(ctx->ev_chunk_done[c], ctx->stream));
         JSDR_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_chunk_done[c], 0));
-        JSDR_CUDA(cudaMemcpyAsync(psd + blk0 * (f->n + 2), f->d_out + blk0 * (f->n + 2), nblk * (f->n + 2) * sizeof(float),
-                                  cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (px) {
+            JSDR_CUDA(cudaMemcpyAsync(px->pixels + blk0 * px->width, f->d_pix + blk0 * px->width,
+                                      nblk * px->width * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+            JSDR_CUDA(cudaMemcpy2DAsync(px->peak + blk0 * 2, 2 * sizeof(float), f->d_out + blk0 * N2 + f->n, N2 * sizeof(float),
+                                        2 * sizeof(float), nblk, cudaMemcpyDeviceToHost, ctx->copy_out));
+        } else {
+            JSDR_CUDA(cudaMemcpyAsync(psd + blk0 * N2, f->d_out + blk0 * N2, nblk * N2 * sizeof(float),
+                                      cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
         if (peak_bin)
             JSDR_CUDA(cudaMemcpyAsync(peak_bin + blk0, f->d_peak + blk0, sizeof(int32_t) * nblk,
                                       cudaMemcpyDeviceToHost, ctx->copy_out));
@@ -1812,6 +1877,7 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
 }
+}  // namespace
 
 // The decimator and matched-filter taps as the kernels use them ((double)(float) of the
 // F-suffixed literals, FUNcubeBPSKDemod.java:27-77), for the reference-pinning tests

@@ -366,7 +366,10 @@ int demod_run(jsdr_demod *d, const float *iq, int S, int64_t chan_stride, float 
     p.dofir = d->dofir;
     p.dodwn = d->dodwn;
     dim3 grid((S + kTile - 1) / kTile, nchan);
-    k_demod<<<grid, kThreads, 0, ctx->stream>>>(p);
+    {
+        ProfScope prof(ctx, JSDR_K_DEMOD, ctx->stream);
+        k_demod<<<grid, kThreads, 0, ctx->stream>>>(p);
+    }
     JSDR_TRY(launched(ctx, "k_demod"));
     if (d->dofir) {   // the delay line only moves when filter() runs (:415-419)
         k_demod_tail<<<nchan, 32, 0, ctx->stream>>>(p);
@@ -530,7 +533,10 @@ extern "C" int jsdr_demod_receive_audio_f32(jsdr_demod *d, const float *iq, int 
     }
     // :409 fmgain = ad.rate / (MODE_NFM==mode ? 5000f : 75000f), int / float in float
     const float fmgain = (float)d->rate / (d->mode == dsp::MODE_NFM ? 5000.0f : 75000.0f);
-    dsp::k_detect<<<d->nchan, 256, 0, ctx->stream>>>(res, S, d->mode, fmgain, d->doagc, d->d_lilq, d->d_det, d_audio, d_ma);
+    {
+        ProfScope prof(ctx, JSDR_K_DETECT, ctx->stream);
+        dsp::k_detect<<<d->nchan, 256, 0, ctx->stream>>>(res, S, d->mode, fmgain, d->doagc, d->d_lilq, d->d_det, d_audio, d_ma);
+    }
     JSDR_TRY(launched(ctx, "k_detect"));
     if (mem == JSDR_MEM_HOST) {
         JSDR_CUDA(cudaMemcpyAsync(audio, d_audio, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -660,7 +666,10 @@ extern "C" int jsdr_fir_filter_i32(jsdr_fir *f, const int32_t *in, int S, int64_
     p.hist_out = f->d_hist[f->hist_cur ^ 1];
     p.out = d_out;
     dim3 grid((S + kThreads - 1) / kThreads, nchan);
-    k_fir_i32<<<grid, kThreads, 0, ctx->stream>>>(p);
+    {
+        ProfScope prof(ctx, JSDR_K_FIR, ctx->stream);
+        k_fir_i32<<<grid, kThreads, 0, ctx->stream>>>(p);
+    }
     JSDR_TRY(launched(ctx, "k_fir_i32"));
     k_fir_tail<<<nchan, 32, 0, ctx->stream>>>(p);
     JSDR_TRY(launched(ctx, "k_fir_tail"));
@@ -732,6 +741,18 @@ __global__ void __launch_bounds__(256) k_waterfall(const float *__restrict__ psd
 }  // namespace dsp
 }  // namespace jsdr
 
+// paintLine for `rows` device-resident PSD rows on a given stream (jsdr_waterfall_rows and the
+// pump's pixel path, bpsk.cu)
+int jsdr_launch_waterfall(jsdr_ctx *ctx, const float *d_psd, int n, int rows, int width, uint32_t peak_rgb,
+                          int32_t *d_pix, cudaStream_t st)
+{
+    if (rows <= 0) return JSDR_OK;
+    dim3 grid((width + 255) / 256, rows);
+    ProfScope prof(ctx, JSDR_K_WATERFALL, st);
+    jsdr::dsp::k_waterfall<<<grid, 256, 0, st>>>(d_psd, n, width, peak_rgb, d_pix);
+    return launched(ctx, "k_waterfall");
+}
+
 extern "C" int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int rows, int width, uint32_t peak_rgb,
                                    int32_t *pixels, int mem)
 {
@@ -756,9 +777,7 @@ extern "C" int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int r
         d_psd = static_cast<const float *>(tmp_in);
         d_pix = static_cast<int32_t *>(tmp_out);
     }
-    dim3 grid((width + 255) / 256, rows);
-    dsp::k_waterfall<<<grid, 256, 0, ctx->stream>>>(d_psd, n, width, peak_rgb, d_pix);
-    int rc = launched(ctx, "k_waterfall");
+    int rc = jsdr_launch_waterfall(ctx, d_psd, n, rows, width, peak_rgb, d_pix, ctx->stream);
     if (mem == JSDR_MEM_HOST) {
         if (rc == JSDR_OK) cudaMemcpyAsync(pixels, d_pix, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

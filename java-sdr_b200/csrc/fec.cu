@@ -537,6 +537,7 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
         // cntBit lives at the end of each TimingState
         const long long *cnt_bit = reinterpret_cast<const long long *>(
             reinterpret_cast<const char *>(b->d_ts) + offsetof(jsdr::bpsk::TimingState, cntBit));
+        ProfScope prof(ctx, JSDR_K_SYNC, ctx->aux);
         fec::k_sync<<<grid, 256, 0, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, b->d_nbits, max_bits, nchan, cnt_bit,
                                                    (int)(sizeof(jsdr::bpsk::TimingState) / sizeof(long long)), f->d_frames,
                                                    f->d_nframes, f->max_frames, f->d_cnt);
@@ -546,10 +547,13 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
     static PerDeviceFlag attr_done;
     if (!attr_done.test_and_set(ctx->device))
         JSDR_CUDA(cudaFuncSetAttribute(fec::k_fec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
-                                                               f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan,
-                                                               f->d_mettab, f->d_rs_par);
-    JSDR_TRY(launched(ctx, "k_fec_decode"));
+    {
+        ProfScope prof(ctx, JSDR_K_FEC, ctx->aux);
+        fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,
+                                                                   f->d_nframes, f->max_frames, f->d_data, f->d_cnt + nchan,
+                                                                   f->d_mettab, f->d_rs_par);
+        JSDR_TRY(launched(ctx, "k_fec_decode"));
+    }
     dim3 g2((fec::HIST + 255) / 256, nchan);
     fec::k_sync_shift<<<g2, 256, 0, ctx->aux>>>(f->d_hist[f->cur], f->d_hist[f->cur ^ 1], b->d_bits, b->d_nbits, max_bits);
     JSDR_TRY(launched(ctx, "k_sync_shift"));

@@ -305,6 +305,7 @@ extern "C" int jsdr_fft_destroy(jsdr_fft *f)
     f->ctx->bind();
     cudaFree(f->d_tw);
     cudaFree(f->d_in);
+    cudaFree(f->d_pix);
     cudaFree(f->d_out);
     cudaFree(f->d_peak);
     cudaFree(f->d_work[0]);

@@ -21,6 +21,8 @@ struct jsdr_fft {
     float *d_out = nullptr;
     int32_t *d_peak = nullptr;
     size_t in_cap = 0, out_cap = 0;
+    int32_t *d_pix = nullptr;        // pixel rows of jsdr_pump_waterfall_s16's host path
+    size_t pix_cap = 0;
 };
 
 namespace jsdr {
@@ -49,6 +51,8 @@ constexpr int kDmTaps = 65;          // MATCHED_FILTER_SIZE
 }  // namespace jsdr
 
 struct jsdr_fec_state;   // fec.cu
+int jsdr_launch_waterfall(jsdr_ctx *ctx, const float *d_psd, int n, int rows, int width, uint32_t peak_rgb,
+                          int32_t *d_pix, cudaStream_t st);   // demod_fir.cu
 
 struct jsdr_bpsk {
     jsdr_ctx *ctx = nullptr;

@@ -116,6 +116,7 @@ _SIGS = {
     "jsdr_fir_filter_i32": [_vp, _vp, _i, _i64, _vp, _i],
     "jsdr_fir_complex_mod_i32": [_vp, _vp, _vp, _vp, _i64, _i],
     "jsdr_pump_receive_s16": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i],
+    "jsdr_pump_waterfall_s16": [_vp, _vp, _vp, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, _i],
     "jsdr_probe_table": [_i, _vp, _i],
     "jsdr_probe_taps": [_vp, _vp],
 }
@@ -240,7 +241,7 @@ class Context:
         _ck(lib().jsdr_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
-    KINDS = ("fft", "mixdecim", "matched", "timing", "scout", "other")
+    KINDS = ("fft", "mixdecim", "matched", "timing", "scout", "other", "demod", "fir", "detect", "waterfall", "sync", "fec")
 
     def profile(self, enable: bool = True):
         """Bracket every kernel launch with CUDA events on its own stream (bench.py)."""
@@ -644,6 +645,14 @@ def pump_receive_s16(f: fft, b: FUNcubeBPSKDemod, raw, nblocks: int, psd, peak_b
     """JavaAudio.run's fan-out (JavaAudio.java:262-304) for [nchan][nblocks*N] s16 IQ; ic/qc are
     the I/Q DC corrections of JavaAudio.java:281-288, seen by both handlers."""
     _ck(lib().jsdr_pump_receive_s16(f.h, b.h, _ptr(raw), nblocks, ic, qc, _ptr(psd), _ptr(peak_bin), mem))
+
+
+def pump_waterfall_s16(f: fft, b: FUNcubeBPSKDemod, raw, nblocks: int, width: int, pixels, peak, peak_bin=None,
+                       mem: int = MEM_HOST, ic: int = 0, qc: int = 0, peak_rgb: int = 0x00ffff):
+    """The pump with waterfall.java's paintLine (:90-107) on the device: pixel rows
+    [nchan*nblocks][width] int32 and peak [nchan*nblocks][2] float32 instead of the PSD."""
+    _ck(lib().jsdr_pump_waterfall_s16(f.h, b.h, _ptr(raw), nblocks, ic, qc, width, peak_rgb, _ptr(pixels), _ptr(peak),
+                                      _ptr(peak_bin), mem))
 
 
 # ---------------------------------------------------------------------------- constant tables

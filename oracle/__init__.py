@@ -305,6 +305,11 @@ def fec_table_probe(which: int, idx: int) -> int:
 
 
 # ---------------------------------------------------------------- CPU baseline drivers
+def baseline_set_fft_mode(mode: int):
+    """0: FFT plan rebuilt per block (what fft.java:194 does); 1: cached plan, modulo-free loops."""
+    lib().orc_baseline_set_fft_mode(int(mode))
+
+
 def baseline_fft_s16(raw: np.ndarray, n: int, rate: int, nthreads: int):
     raw = np.ascontiguousarray(raw, dtype=np.int16).ravel()
     nblocks = raw.size // (2 * n)

@@ -146,6 +146,10 @@ int  orc_rs_decode(uint8_t data[255]);                            /* decode_rs_8
 
 /* ---- CPU baseline drivers (pthreads over channels / blocks) ------------ */
 /* returns the number of threads used */
+/* 0 (default): the FFT plan and twiddle table are rebuilt for every block, as fft.java:194 does
+ * (new FloatFFT_1D per receive); 1: built once per thread and length, modulo-free loops — more
+ * favourable to the CPU than the reference's own code (bench.py's CPU arm uses 1) */
+void orc_baseline_set_fft_mode(int mode);
 int orc_baseline_fft_s16(const int16_t *raw, int nblocks, int n, int rate, float *psd, int nthreads);
 /* the benchmark pipeline per (channel, block): JavaAudio conversion, fft.receive
  * (float plan rebuilt per block) and the tuner + decimator */

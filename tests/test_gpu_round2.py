@@ -126,3 +126,43 @@ def test_pump_applies_iq_correction(ctx):
         check_psd(psd[c * nblk + 1], O.s16_to_float(raw[c, 2 * n:4 * n], ic=ic, qc=qc), rate, n)
     f.close()
     bank.close()
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_pump_waterfall_pixels_equal_paintline_of_the_psd(ctx, mem):
+    """jsdr_pump_waterfall_s16: the pixel rows are waterfall.paintLine (waterfall.java:90-107) of
+    exactly the PSD rows jsdr_pump_receive_s16 returns, the two trailing floats are psd[N] and
+    psd[N+1] (fft.java:223-224), and the tuner bank behind it is unchanged."""
+    rate, nch, n, nblk, width = 96000, 40, 1024, 3, 400
+    rng = np.random.default_rng(8)
+    raw = rng.integers(-20000, 20000, (nch, 2 * n * nblk)).astype(np.int16)
+    tun = rng.uniform(2000, 40000, nch)
+    adsc = J.AudioDescriptor(rate)
+    f = J.fft(ctx, None, adsc, max_batch=nch * nblk, n=n)
+    b1 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=n * nblk, stages=1)
+    b2 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=n * nblk, stages=1)
+    psd = np.empty((nch * nblk, n + 2), np.float32)
+    J.pump_receive_s16(f, b1, raw, nblk, psd)
+    pix = np.zeros((nch * nblk, width), np.int32)
+    peak = np.zeros((nch * nblk, 2), np.float32)
+    pk = np.zeros(nch * nblk, np.int32)
+    if mem == "host":
+        J.pump_waterfall_s16(f, b2, raw, nblk, width, pix, peak, pk)
+    else:
+        d_raw, d_pix, d_peak, d_pk = (ctx.dev_alloc(x.nbytes) for x in (raw, pix, peak, pk))
+        d_raw.upload(raw)
+        J.pump_waterfall_s16(f, b2, d_raw, nblk, width, d_pix, d_peak, d_pk, mem=J.MEM_DEVICE)
+        ctx.sync()
+        pix = d_pix.download(np.int32, pix.size).reshape(pix.shape)
+        peak = d_peak.download(np.float32, peak.size).reshape(peak.shape)
+        pk = d_pk.download(np.int32, pk.size)
+        for d in (d_raw, d_pix, d_peak, d_pk):
+            d.free()
+    assert np.array_equal(peak, psd[:, n:])
+    for r in (0, 1, 57, nch * nblk - 1):
+        assert np.array_equal(pix[r], O.waterfall_row(psd[r], width)), r
+    assert np.array_equal(pix, J.waterfall_rows(ctx, psd, width))
+    assert np.array_equal(pk, psd[:, :n].argmax(axis=1))
+    assert np.array_equal(b1.read_ds(), b2.read_ds())
+    for h in (f, b1, b2):
+        h.close()

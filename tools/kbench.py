@@ -2,6 +2,7 @@
 """Kernel-level timings on one GPU (CUDA events on the library's stream).
   python tools/kbench.py mix   [nchan] [S]      tuner+decimator: tile / stream f64 / stream f32
   python tools/kbench.py fft   [n ...]          FFT+PSD per length (s16 and f32 input)
+  python tools/kbench.py other                  demod.java FIR+NCO, detectors, fir.java int FIR, waterfall rows, frame stage
 Prints achieved GB/s of algorithmic bytes and the fraction of MEASURED_PEAKS.json."""
 import json
 import os
@@ -155,6 +156,100 @@ def pump(nchan=4096, nblk=128, n=4096, rate=192000, reps=6):
     ctx.close()
 
 
+def other(nchan=1024, S=131072, rate=192000):
+    """The remaining kernels of the path, device-resident, per-kernel CUDA-event times and the
+    achieved GB/s of their algorithmic bytes: demod.java FIR + NCO (:410-434), its detectors
+    + AGC + s16 (:448-481), fir.java's int FIR (:198-211), waterfall.java's paintLine (:90-107),
+    and the frame stage (sync correlator + FECDecode, FUNcubeBPSKDemod.java:553-574)."""
+    import ctypes as C
+    L = J.lib()
+    ctx = J.Context(0)
+    rng = np.random.default_rng(4)
+    adsc = J.AudioDescriptor(rate)
+
+    def timed(kind, fn, bytes_, label, reps=5):
+        for _ in range(2):
+            fn()
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_read()
+        for _ in range(reps):
+            fn()
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        ms = prof[kind][0] / max(prof[kind][1], 1)
+        gbs = bytes_ / ms / 1e6
+        print(f"{label:58s} {ms:8.4f} ms/launch  {gbs:7.1f} GB/s  frac {gbs / PEAK:.3f}", flush=True)
+
+    # ---- demod.java: 21-tap complex FIR (float, reference order) + float NCO, then detectors
+    tile = rng.uniform(-1, 1, (16, 2 * S)).astype(np.float32)
+    d_iq = ctx.dev_alloc(nchan * S * 8)
+    for c0 in range(0, nchan, 16):
+        d_iq.upload(tile[: min(16, nchan - c0)], offset=c0 * S * 8)
+    d_out = ctx.dev_alloc(nchan * S * 8)
+    dm = J.demod(ctx, adsc, nchan=nchan, max_block=S)
+    for c in range(nchan):
+        dm.weights(3000, 6000, chan=c)
+    dm.set_flags(True, True)
+    timed("demod", lambda: J._ck(L.jsdr_demod_receive_f32(dm.h, J._ptr(d_iq), S, S, J._ptr(d_out), J.MEM_DEVICE)),
+          nchan * S * 16, f"demod FIR+NCO      nchan={nchan} S={S} (8 B in + 8 B out)")
+    d_aud = ctx.dev_alloc(nchan * S * 2)
+    d_ma = ctx.dev_alloc(nchan * 8)
+    for mode, name in ((2, "AM"), (3, "NFM")):
+        dm.set_mode(mode, True)
+        timed("detect", lambda: J._ck(L.jsdr_demod_receive_audio_f32(dm.h, J._ptr(d_iq), S, S, J._ptr(d_aud), J._ptr(d_ma), J.MEM_DEVICE)),
+              nchan * S * 10, f"demod detect {name:3s}+AGC+s16 nchan={nchan} S={S} (8 B in + 2 B out)")
+    dm.close()
+    # ---- fir.java: int samples x double taps
+    f = J.fir(ctx, float(rate), nchan=nchan, max_block=S)
+    for c in range(nchan):
+        f.weights(3000, 6000, chan=c)
+    d_ii = ctx.dev_alloc(nchan * S * 4)
+    ti = rng.integers(-30000, 30000, (16, S)).astype(np.int32)
+    for c0 in range(0, nchan, 16):
+        d_ii.upload(ti[: min(16, nchan - c0)], offset=c0 * S * 4)
+    timed("fir", lambda: J._ck(L.jsdr_fir_filter_i32(f.h, J._ptr(d_ii), S, S, J._ptr(d_out), J.MEM_DEVICE)),
+          nchan * S * 8, f"fir.java int FIR    nchan={nchan} S={S} (4 B in + 4 B out)")
+    f.close()
+    # ---- waterfall rows from a resident PSD
+    n, rows, width = 4096, 65536, 1024
+    d_psd = ctx.dev_alloc(rows * (n + 2) * 4)
+    prow = rng.uniform(-100, 0, (64, n + 2)).astype(np.float32)
+    for r0 in range(0, rows, 64):
+        d_psd.upload(prow, offset=r0 * (n + 2) * 4)
+    d_pix = ctx.dev_alloc(rows * width * 4)
+    timed("waterfall", lambda: J._ck(L.jsdr_waterfall_rows(ctx.h, J._ptr(d_psd), n, rows, width, 0x00ffff, J._ptr(d_pix), J.MEM_DEVICE)),
+          rows * ((n + 2) * 4 + width * 4), f"waterfall rows      rows={rows} n={n} width={width}")
+    for d in (d_iq, d_out, d_aud, d_ma, d_ii, d_psd, d_pix):
+        d.free()
+    # ---- frame stage: config-2 frames on one shared stream, every tuner of the bank on the signal
+    import oracle as O
+    from oracle import siggen
+    r2 = 96000
+    nt = 256
+    pl = siggen.random_payloads(3)
+    sig = siggen.make_iq_s16(pl, rate=r2, ebn0_db=13.0, pad_to=9600)
+    blk = 9600 * 8
+    sig = sig[: (sig.size // (2 * blk)) * 2 * blk]
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(r2), tuning=np.full(nt, 12000.0), max_block=blk, stages=3)
+    mett = np.array([[O.fec_table_probe(6 + r, i) for i in range(256)] for r in range(2)], dtype=np.int16)
+    bank.enable_fec(mett, max_frames=nt * 2)
+    ctx.profile(True)
+    ctx.profile_read()
+    nframes = 0
+    for k in range(sig.size // (2 * blk)):
+        bank.receive_raw(sig[2 * k * blk: 2 * (k + 1) * blk], shared=True)
+        nframes += len(bank.read_frames())
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    per = {k: (round(v[0], 3), v[1]) for k, v in prof.items() if v[1]}
+    fec_ms, fec_n = prof["fec"]
+    print(f"frame stage: {nt} tuners x {sig.size // 2} samples, {nframes} frames decoded; k_fec_decode {fec_ms:.3f} ms over {fec_n} launches "
+          f"({1000 * fec_ms / max(nframes, 1):.1f} us per frame at {nt} frames per launch), k_sync {prof['sync'][0]:.3f} ms; all kernels (ms, launches): {per}", flush=True)
+    bank.close()
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mix"
     if what == "mix":
@@ -164,6 +259,8 @@ if __name__ == "__main__":
         pump(*[int(x) for x in sys.argv[2:]])
     elif what == "chain":
         chain(*[int(x) for x in sys.argv[2:]])
+    elif what == "other":
+        other(*[int(x) for x in sys.argv[2:]])
     else:
         fft([int(x) for x in sys.argv[2:]] or [256, 1024, 4096, 9600, 16384, 19200])
 
