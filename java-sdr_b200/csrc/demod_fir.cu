@@ -722,8 +722,8 @@ namespace dsp {
 __global__ void __launch_bounds__(256) k_waterfall(const float *__restrict__ psd, int n, int width, unsigned peak_rgb,
                                                    int32_t *__restrict__ pix)
 {
-    const int row = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x;                                    // rows in x: a batch has more than 65535 of them
+    const int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= width) return;
     const float *a = psd + (size_t)row * (n + 2);
     const float step = __fdiv_rn((float)n, (float)width);          // :61 (float)(length-2)/(float)getWidth()
@@ -747,7 +747,7 @@ int jsdr_launch_waterfall(jsdr_ctx *ctx, const float *d_psd, int n, int rows, in
                           int32_t *d_pix, cudaStream_t st)
 {
     if (rows <= 0) return JSDR_OK;
-    dim3 grid((width + 255) / 256, rows);
+    dim3 grid(rows, (width + 255) / 256);
     ProfScope prof(ctx, JSDR_K_WATERFALL, st);
     jsdr::dsp::k_waterfall<<<grid, 256, 0, st>>>(d_psd, n, width, peak_rgb, d_pix);
     return launched(ctx, "k_waterfall");

@@ -166,3 +166,13 @@ def test_pump_waterfall_pixels_equal_paintline_of_the_psd(ctx, mem):
     assert np.array_equal(b1.read_ds(), b2.read_ds())
     for h in (f, b1, b2):
         h.close()
+
+
+def test_waterfall_rows_more_than_65535(ctx):
+    """A pump batch has nchan*nblocks rows: far beyond the 65535 limit of a grid's y dimension."""
+    n, rows, width = 128, 70000, 64
+    rng = np.random.default_rng(1)
+    psd = rng.uniform(-100, 0, (rows, n + 2)).astype(np.float32)
+    pix = J.waterfall_rows(ctx, psd, width)
+    for r in (0, 65535, 65536, rows - 1):
+        assert np.array_equal(pix[r], O.waterfall_row(psd[r], width)), r
