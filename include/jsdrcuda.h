@@ -259,6 +259,11 @@ int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const int32_t *b, 
  */
 int jsdr_probe_table(int which, int32_t *out, int n);
 int jsdr_probe_taps(double ds27[27], double dm65[65]);
+/* The exact wrap thresholds of the tuner-phase replay for one increment (0 < inc < 3.1):
+ * th1 = the largest double p in [0, 2pi] for which `tuPhase += inc; if (tuPhase > 2pi)`
+ * (FUNcubeBPSKDemod.java:384-386) does NOT wrap from p, th2 the same for the second of two
+ * steps whose first did not wrap (-1: wraps from every phase).  Host only. */
+int jsdr_probe_scout_thresholds(double inc, double *th1, double *th2);
 
 /* ------------------------------------------------------------------ the pump
  * JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: every channel's

@@ -1890,3 +1890,14 @@ extern "C" int jsdr_probe_taps(double *ds27, double *dm65)
     for (int i = 0; i < 65; i++) dm65[i] = (double)jsdr::bpsk::kDmFilterF[i];
     return JSDR_OK;
 }
+
+// The exact wrap thresholds the phase scout uses for one tuner increment (scout_thresholds):
+// host only, for tests/test_scout_thresholds.py, which checks on the CPU that `p > th1` / `p > th2`
+// ARE the reference's comparisons (FUNcubeBPSKDemod.java:385) for every double around them.
+extern "C" int jsdr_probe_scout_thresholds(double inc, double *th1, double *th2)
+{
+    JSDR_REQUIRE(th1 && th2, JSDR_EINVAL, "null argument");
+    JSDR_REQUIRE(inc > 0.0 && inc < 3.1, JSDR_EINVAL, "the pair form covers 0 < inc < 3.1");
+    scout_thresholds(inc, *th1, *th2);
+    return JSDR_OK;
+}

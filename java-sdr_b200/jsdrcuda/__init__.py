@@ -119,6 +119,7 @@ _SIGS = {
     "jsdr_pump_waterfall_s16": [_vp, _vp, _vp, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, _i],
     "jsdr_probe_table": [_i, _vp, _i],
     "jsdr_probe_taps": [_vp, _vp],
+    "jsdr_probe_scout_thresholds": [_d, C.POINTER(_d), C.POINTER(_d)],
 }
 EXPORTS = sorted(list(_SIGS) + ["jsdr_last_error"])
 
@@ -667,6 +668,13 @@ def probe_table(name: str) -> np.ndarray:
     out = np.empty(n, dtype=np.int32)
     _ck(lib().jsdr_probe_table(which, _ptr(out), n))
     return out
+
+
+def probe_scout_thresholds(inc: float):
+    """(th1, th2) of the tuner-phase replay for one increment (jsdr_probe_scout_thresholds)."""
+    a, b = _d(), _d()
+    _ck(lib().jsdr_probe_scout_thresholds(inc, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def probe_taps():
