@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--e2e-channels", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--main-only", action="store_true",
+                    help="only the timed step (for ncu runs): skips the variants, latency, e2e and CPU legs; prints a short line")
     return ap.parse_args()
 
 
@@ -296,6 +298,17 @@ def main():
     fft_ms = kern["fft"][0] / max(kern["fft"][1], 1)
     mix_ms = kern["mixdecim"][0] / max(kern["mixdecim"][1], 1)
     scout_ms = kern["scout"][0] / max(kern["scout"][1], 1)
+
+    if a.main_only:
+        if rank == 0:
+            print(json.dumps({"main_only": True, "ms_per_step": round(ms / a.steps, 4), "fft_ms": round(fft_ms, 4),
+                              "mixdecim_ms": round(mix_ms, 4), "scout_ms": round(scout_ms, 4), "gpu_launches": int(launches)}), flush=True)
+        for h in (f, bank):
+            h.close()
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- the FFT kernel with the SMs to itself (no phase scout beside it), for the record
     ctx.sync()
