@@ -108,8 +108,10 @@ __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
         }
         if (p.dodwn) {
             float car = sCar[(i / kChunk) * (kChunk + 1) + (i % kChunk)];
-            float ci = (float)cos((double)car);            // :425
-            float cq = (float)sin((double)car);            // :426
+            double dc, dsn;                                // :425-426 (float)Math.cos(car), (float)Math.sin(car):
+            sincos((double)car, &dsn, &dc);                // one argument reduction for both
+            float ci = (float)dc;
+            float cq = (float)dsn;
             float a = si, b = sq;
             si = __fsub_rn(__fmul_rn(a, ci), __fmul_rn(b, cq));   // :432
             sq = __fadd_rn(__fmul_rn(a, cq), __fmul_rn(b, ci));   // :433
