@@ -1120,7 +1120,9 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     sp.ncw = (mp.nchan + 31) / 32;
     // one CTA per SM, warps loop over segments; the SMs the phase scout needs (on the
     // high-priority side stream) are left free so that the two never share an SM.  Segments:
-    // about three per resident warp, their count chosen so that the last wave is full.
+    // about ten per resident warp (round 2; three before): SMs that join late, when the scout
+    // lets go of them, and the last wave then balance to within a tenth of a warp's share, for
+    // (NQ-1)/R = 2 % of warm-up periods (3.91 -> 3.72 ms in the pump, profiles/r02_stream_segs.txt).
     const int scout_ctas = (mp.nchan + scout_threads(b) - 1) / scout_threads(b);
     // stand-alone, the replay of the next block runs beside this kernel: leave it its SMs.  In the
     // pump it runs beside the FFT that precedes this kernel and is normally done by now, so every SM
@@ -1128,7 +1130,9 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
     sp.grid = b->in_pump ? b->ctx->sm_count : std::max(b->ctx->sm_count - scout_ctas, b->ctx->sm_count / 2);
     sp.warps_per_cta = (FMT == FMT_S16) ? stream::kWarps : stream::kWarpsF32;
     const int resident = sp.grid * sp.warps_per_cta;
-    int nseg = std::max(1, 3 * resident / sp.ncw);
+    static int segs_per_warp = 0;
+    if (!segs_per_warp) segs_per_warp = env_int("JSDR_STREAM_SEGS", 1, 64, 10);   // (tuning aid)
+    int nseg = std::max(1, segs_per_warp * resident / sp.ncw);
     int R = (mp.NO + nseg - 1) / nseg;
     if (R < 64) R = 64;
     sp.R = R;
