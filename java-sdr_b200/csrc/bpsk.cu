@@ -1761,29 +1761,39 @@ extern "C" int jsdr_bpsk_ds_device_ptr(jsdr_bpsk *b, double **dev_ptr)
 
 // ------------------------------------------------------------------ the pump
 namespace {
-struct PumpJob {
-    jsdr_fft *f;
-    int batch, ic, qc;
-    float *d_psd;
-    int32_t *d_peak;
-};
-int pump_fft(void *user, const void *d_in)
-{
-    PumpJob *j = static_cast<PumpJob *>(user);
-    jsdr_ctx *ctx = j->f->ctx;
-    return fft::launch(j->f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream);
-}
-}  // namespace
-
-// JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: each channel's
-// blocks go to the fft handler and to the tuner bank.
-namespace {
 struct PumpPixels {          // jsdr_pump_waterfall_s16: pixel rows and the two trailing floats instead of the PSD
     int width;
     uint32_t rgb;
     int32_t *pixels;         // [batch][width]
     float *peak;             // [batch][2]: psd[N] (peak Hz), psd[N+1] (peak dB)
 };
+struct PumpJob {
+    jsdr_fft *f;
+    int batch, ic, qc;
+    float *d_psd;
+    int32_t *d_peak;
+    const PumpPixels *px;    // device-resident pixel path: paintLine and the maxima behind the FFT
+};
+// runs inside bpsk_receive after its fork, so that the next block's phase replay (side stream)
+// starts beside this FFT and not behind it
+int pump_fft(void *user, const void *d_in)
+{
+    PumpJob *j = static_cast<PumpJob *>(user);
+    jsdr_fft *f = j->f;
+    jsdr_ctx *ctx = f->ctx;
+    JSDR_TRY(fft::launch(f, d_in, fft::IN_S16, j->batch, j->d_psd, j->d_peak, fft::OUT_PSD, j->ic, j->qc, ctx->stream));
+    if (j->px) {
+        JSDR_TRY(jsdr_launch_waterfall(ctx, j->d_psd, f->n, j->batch, j->px->width, j->px->rgb, j->px->pixels, ctx->stream));
+        JSDR_CUDA(cudaMemcpy2DAsync(j->px->peak, 2 * sizeof(float), j->d_psd + f->n, (f->n + 2) * sizeof(float),
+                                    2 * sizeof(float), (size_t)j->batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return JSDR_OK;
+}
+}  // namespace
+
+// JavaAudio.run's fan-out (JavaAudio.java:262-304) for a batch: each channel's
+// blocks go to the fft handler and to the tuner bank.
+namespace {
 int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc, float *psd,
                  int32_t *peak_bin, int mem, const PumpPixels *px);
 }  // namespace
@@ -1826,6 +1836,7 @@ int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int
     job.batch = (int)batch;
     job.ic = ic;                                   // JavaAudio.java:281-288: both handlers see the corrected samples
     job.qc = qc;
+    job.px = nullptr;
     const size_t psd_elems = (size_t)batch * (f->n + 2);
     if (mem == JSDR_MEM_DEVICE && !px) {
         job.d_psd = psd;
@@ -1847,12 +1858,9 @@ int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int
     if (mem == JSDR_MEM_DEVICE) {                      // pixel rows from a resident batch: FFT, paintLine, tuner bank
         job.d_psd = f->d_out;
         job.d_peak = peak_bin ? peak_bin : f->d_peak;
-        JSDR_TRY(fft::launch(f, raw, fft::IN_S16, (int)batch, job.d_psd, job.d_peak, fft::OUT_PSD, ic, qc, ctx->stream));
-        JSDR_TRY(jsdr_launch_waterfall(ctx, f->d_out, f->n, (int)batch, px->width, px->rgb, px->pixels, ctx->stream));
-        JSDR_CUDA(cudaMemcpy2DAsync(px->peak, 2 * sizeof(float), f->d_out + f->n, N2 * sizeof(float), 2 * sizeof(float),
-                                    (size_t)batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        job.px = px;
         b->in_pump = 1;
-        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, ic, qc, mem);
+        const int rc = bpsk_receive<FMT_S16>(b, raw, (int)S, S, ic, qc, mem, pump_fft, &job);
         b->in_pump = 0;
         return rc;
     }
