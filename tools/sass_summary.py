@@ -46,7 +46,7 @@ def main():
         print("  " + "  ".join(f"{k}:{v}" for k, v in hist.most_common(28)))
         blk = [t for _, t in ins if re.match(r"(@!?U?P\d+\s+)?(UBLK|UTMA|SYNCS|LDGSTS|REDUX|SHFL|VOTE|MATCH)", t)]
         if blk:
-            print("  bulk-copy / warp-collective instructions: " + "; ".join(sorted(set(re.sub(r"\s+", " ", b)[:48] for b in blk))[:10]))
+            print("  bulk-copy / warp-collective instructions: " + "; ".join(sorted(set(re.sub(r"\s+", " ", re.sub(r"^@!?U?P\d+\s+", "", b)).split(",")[0][:40] for b in blk))[:16]))
         # the hot loop: the backward branch that spans the most floating-point instructions
         best = None
         for i, (addr, t) in enumerate(ins):
