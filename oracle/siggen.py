@@ -49,9 +49,10 @@ def interpolate(x: np.ndarray, factor: int) -> np.ndarray:
 
 def make_iq_s16(payloads, rate: int = 96000, carrier_hz: float = 13200.0,
                 amplitude: float = 0.25, ebn0_db: float | None = 16.0,
-                noise_seed: int = 20261019, pad_to: int | None = None) -> np.ndarray:
-    """Frames back to back -> interleaved s16 IQ at `rate` (int16[2*n])."""
-    syms = np.concatenate([frame_symbols(p) for p in payloads])
+                noise_seed: int = 20261019, pad_to: int | None = None, symbols=None) -> np.ndarray:
+    """Frames back to back -> interleaved s16 IQ at `rate` (int16[2*n]).  `symbols`: ready-made
+    5200-symbol frames instead of payloads (tests that inject errors behind the convolutional code)."""
+    syms = np.concatenate([frame_symbols(p) for p in payloads] if symbols is None else list(symbols))
     bb = dbpsk_baseband_9600(syms)
     x = interpolate(bb, rate // 9600)
     x = x / np.max(np.abs(x)) * amplitude

@@ -103,17 +103,29 @@ def rs_parity_map(alpha_to, index_of, rs_poly):
     return par
 
 
-def reencode_symbols(out, par, gf, scrambler, sync):
-    """The 5200 symbols (0/1) encode_FEC40 would produce, position by position."""
+def rs_parity(data128, par, gf):
+    """The 32 parity bytes of one RS(160,128) block (lowest-order first), by the linear map."""
+    out = []
+    for k in range(32):
+        p = 0
+        for i in range(128):
+            p ^= gf.mul(int(data128[i]), par[i][k])
+        out.append(p)
+    return out
+
+
+def symbols_from_blocks(blocks, scrambler, sync):
+    """The 5200 channel symbols (0/1) of a frame whose two RS blocks are given as 160 bytes each
+    (128 data + 32 parity) — NOT necessarily code words: the frame-stage tests inject symbol
+    errors here, behind the convolutional code.  Byte order of the stream the convolutional
+    encoder sees (FECDecoder.java:614-671): data byte i = blocks[i & 1][i >> 1], then parity byte
+    256 + 2k + r = blocks[r][128 + k]; scrambled; position by position as in fec.cu."""
     enc = [0] * 324
-    for lane in range(32):
-        for r in range(2):
-            p = 0
-            for i in range(128):
-                p ^= gf.mul(int(out[2 * i + r]), par[i][lane])
-            enc[256 + 2 * lane + r] = p ^ scrambler[256 + 2 * lane + r]
     for i in range(256):
-        enc[i] = int(out[i]) ^ scrambler[i]
+        enc[i] = int(blocks[i & 1][i >> 1]) ^ scrambler[i]
+    for k in range(32):
+        for r in range(2):
+            enc[256 + 2 * k + r] = int(blocks[r][128 + k]) ^ scrambler[256 + 2 * k + r]
     sym = np.zeros(SYMS, dtype=np.uint8)
     for p in range(SYMS):
         row, col = divmod(p, ROWS)
@@ -128,3 +140,12 @@ def reencode_symbols(out, par, gf, scrambler, sync):
                 win = (two >> (7 - (n & 7))) & 0x7F
                 sym[p] = (1 - (bin(win & CPOLYB).count("1") & 1)) if (k & 1) else (bin(win & CPOLYA).count("1") & 1)
     return sym
+
+
+def reencode_symbols(out, par, gf, scrambler, sync):
+    """The 5200 symbols (0/1) encode_FEC40 would produce for 256 data bytes, position by position."""
+    blocks = []
+    for r in range(2):
+        d = [int(out[2 * i + r]) for i in range(128)]
+        blocks.append(d + rs_parity(d, par, gf))
+    return symbols_from_blocks(blocks, scrambler, sync)

@@ -92,3 +92,51 @@ def test_frame_stage_many_channels_ragged_blocks(ctx):
         mine = [f for f in frames if f[0] == c and f[2] >= 0]
         assert len(mine) == 2 and all(np.array_equal(f[3], p) for f, p in zip(mine, pl)), c
     bank.close()
+
+
+@pytest.mark.parametrize("nerr", [(0, 0), (5, 16), (16, 1), (17, 0), (20, 3), (40, 40)])
+def test_rs_decoder_branches_on_crafted_frames(ctx, nerr):
+    """Frames whose two RS(160,128) blocks carry a chosen number of symbol errors BEHIND the
+    convolutional code (the Viterbi decoder sees a clean channel and hands the corrupted words to
+    the RS stage): clean, corrected, at the capacity of 16, and beyond it — where the outcome is
+    whatever the reference's Berlekamp-Massey / root search / Forney sequence yields (failure
+    -1, or a miscorrection).  The warp-parallel decoder must return exactly what the oracle's
+    restatement of FECDecoder.java:325-519 returns on the same bits: frame list, error counts,
+    payload bytes."""
+    import rs_warp_model as M
+    alpha, index, poly = (J.probe_table(t).tolist() for t in ("ALPHA_TO", "INDEX_OF", "RS_poly"))
+    gf = M.GF(alpha, index)
+    par = M.rs_parity_map(alpha, index, poly)
+    scr, sync = J.probe_table("Scrambler").tolist(), J.probe_table("SYNC_VECTOR").tolist()
+    rng = np.random.default_rng(1000 + 41 * nerr[0] + nerr[1])
+    frames = []
+    for _ in range(2):
+        blocks = []
+        for r in range(2):
+            d = rng.integers(0, 256, 128).tolist()
+            cw = d + M.rs_parity(d, par, gf)
+            for q in rng.choice(160, nerr[r], replace=False):
+                cw[q] ^= int(rng.integers(1, 256))
+            blocks.append(cw)
+        frames.append(M.symbols_from_blocks(blocks, scr, sync))
+    sig = siggen.make_iq_s16(None, rate=96000, ebn0_db=None, pad_to=9600, symbols=frames)
+    fbuf = O.s16_to_float(sig)
+    adsc = J.AudioDescriptor(96000)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0])
+    bank.enable_fec(mettab(), max_frames=8)
+    orc = O.Bpsk(96000, 12000.0)
+    got, allbits = [], []
+    for k in range(fbuf.size // (2 * adsc.samples)):
+        blk = fbuf[2 * k * adsc.samples: 2 * (k + 1) * adsc.samples]
+        bank.receive(blk)
+        got += bank.read_frames()
+        allbits.append(orc.receive(blk)["bits"])
+    ref = oracle_frames(np.concatenate(allbits))
+    assert len(ref) >= 2 and len(got) == len(ref)
+    for (ch, at, err, data), (rat, rerr, rdata) in zip(got, ref):
+        assert at == rat and err == rerr, (nerr, err, rerr)
+        if rerr >= 0:
+            assert np.array_equal(data, rdata)
+    if max(nerr) <= 16:
+        assert all(g[2] >= 0 for g in got)          # within capacity: decoded
+    bank.close()
