@@ -65,7 +65,13 @@ final class CudaFUNcubeBPSKDemod {
 
 	/** Called from FUNcubeBPSKDemod.setup() (:192-209).  mettab = FECDecoder's own metric table. */
 	static CudaFUNcubeBPSKDemod attach(CudaFUNcubeBPSKDemod old, ILogger logger, AudioDescriptor adsc, int[][] mettab) {
-		JsdrCuda.Context ctx = JsdrCuda.shared(logger);
+		JsdrCuda.Context ctx;
+		try {
+			ctx = JsdrCuda.shared(logger);                       // first use loads libjsdrcuda.so (static initialiser)
+		} catch (Throwable t) {                                  // library absent: ExceptionInInitializerError / NoClassDefFoundError
+			logger.statusMsg("libjsdrcuda.so not in use: " + t);
+			return null;
+		}
 		if (ctx == null) return null;
 		int samples = adsc.blen / adsc.size;                                         // :194
 		if (old != null && old.rate == adsc.rate && old.samples == samples && !old.failed) return old;

@@ -40,7 +40,13 @@ final class CudaFft {
 	 *  the old one if nothing changed, a new one (the old one's handle and pinned buffers
 	 *  released) otherwise, or null when the library is not installed. */
 	static CudaFft attach(CudaFft old, ILogger logger, AudioDescriptor adsc) {
-		JsdrCuda.Context ctx = JsdrCuda.shared(logger);
+		JsdrCuda.Context ctx;
+		try {
+			ctx = JsdrCuda.shared(logger);                       // first use loads libjsdrcuda.so (static initialiser)
+		} catch (Throwable t) {                                  // library absent: ExceptionInInitializerError / NoClassDefFoundError
+			logger.statusMsg("libjsdrcuda.so not in use: " + t);
+			return null;
+		}
 		if (ctx == null) return null;
 		int n = adsc.blen / adsc.size;                           // fft.java:67
 		if (old != null && old.n == n && old.rate == adsc.rate && !old.failed) return old;
