@@ -1,6 +1,8 @@
 // fft_inst.cuh — one translation unit per FFT length includes this with
 // JSDR_FFT_N etc. defined, so the plans compile in parallel.
 #pragma once
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "fft_kernels.cuh"
@@ -13,20 +15,23 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
 {
     static PerDeviceFlag attr_done;
     auto kern = fft_kernel<P, IN, OUT>;
+    // JSDR_FFT_EXTRA_SMEM_KB: unused shared memory added to every CTA (occupancy experiments only)
+    static const size_t extra = []() { const char *e = getenv("JSDR_FFT_EXTRA_SMEM_KB"); return e ? (size_t)std::max(0, atoi(e)) * 1024 : (size_t)0; }();
+    const size_t smem = std::min(P::SMEM + extra, (size_t)227 * 1024);
     if (!attr_done.test_and_set(ctx->device))
-        JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+        JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
     static int per_sm = 0;                        // a property of the kernel and sm_100a, not of the device index
     if (!per_sm) {
-        JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, P::SMEM));
+        JSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T, smem));
         per_sm = std::max(1, per_sm);
     }
     Args b = a;
     if constexpr (P::PERSIST && IN == IN_S16) grid = std::min(grid, per_sm * ctx->sm_count);   // resident CTAs loop over the blocks
     else b.pf_dist = ctx->l2_prefetch * per_sm * ctx->sm_count;                // L2 look-ahead distance in CTAs
     ProfScope prof(ctx, JSDR_K_FFT, st);
-    kern<<<grid, P::T, P::SMEM, st>>>(b);
+    kern<<<grid, P::T, smem, st>>>(b);
     return launched(ctx, "fft_kernel");
 }
 
