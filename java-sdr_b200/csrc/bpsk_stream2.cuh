@@ -11,15 +11,21 @@
 //   * the ring holds four PERIODS per row, not two 32-sample chunks: period t of the segment lives
 //     in slot t & 3, 80 bytes per row, row pitch 84 words (4 x odd: the 128-bit reads of 32 lanes,
 //     each in its own row, fall in distinct bank quads);
-//   * a period is staged three periods ahead by 16-byte cp.async (LDGSTS) copies straight from
-//     global to shared memory — five per lane per period, no registers, no STS — tracked with
-//     cp.async groups; the slot it lands in was read one period ago;
+//   * a period is staged three periods ahead by ONE bulk (TMA-engine) copy per lane — its own
+//     row's 80 bytes, cp.async.bulk global -> shared, no registers, no STS — completing on an
+//     mbarrier per slot and warp (expect_tx by lane 0, try_wait on the slot's phase parity by
+//     all); the slot it lands in was read one period ago;
 //   * a lane reads its period as five LDS.128 at fixed offsets from the slot base: no ring
 //     masking, no mirror, a quarter of the load instructions.
 // The copies need the period's first sample on a 16-byte boundary in every row: the input base and
 // the channel stride 16-byte aligned and (first sample index) % 4 == 0, which holds whenever the
 // block lengths are multiples of 4 (dsCnt then only takes multiples of 4).  The host checks and
 // falls back to the chunk-ring kernel otherwise (and for I/Q correction, float input, D = 10).
+// MEASURED SLOWER than the chunk ring (5.03 against 3.90 ms per 2^31 samples in the pump; 4.60 ms
+// with five 16-byte cp.async copies per lane instead of the bulk copy): 107 M copies of 80 bytes per
+// step are the wrong granularity for the copy engines.  It is therefore opt-in
+// (jsdr_bpsk_set_kernel(JSDR_KERNEL_PRING) / JSDR_PRING=1) and kept as the record of that experiment
+// (DESIGN.md section 9), bit-identical to the default kernel and tested as such.
 // Periods that reach outside the block (history before sample 0, the zero tail after the last
 // sample) are staged synchronously with bounds checks and run the sample-by-sample body.
 #pragma once
@@ -37,13 +43,6 @@ constexpr size_t p_smem_bytes()
 {
     return (size_t)kTabBytes + (size_t)kPWarps * (32 * p_pitch<DD>() * 4 + kPSlots * 8);
 }
-
-__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- bulk (TMA-engine) copies tracked by an mbarrier: one 16-byte-aligned row segment per lane
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
@@ -101,9 +100,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 1) k_mixdecim_pring(const Params
     constexpr int NQ = (NTAPS + DD - 1) / DD;
     constexpr int PITCH = p_pitch<DD>();                 // words
     constexpr int H = NTAPS - 1;
-    constexpr int QPP = DD / 4;                          // 16-byte pieces per row per period
-    constexpr int NPIECE = 32 * QPP;                     // pieces per warp per period
-    constexpr int CPL = (NPIECE + 31) / 32;              // copies per lane per period
+    constexpr int QPP = DD / 4;                          // 128-bit reads per lane per period
     constexpr int AHEAD = kPSlots - 1;                   // periods staged ahead of the one in use
     static_assert(DD % 4 == 0 && DD <= 32, "period");
     static_assert(NTAPS <= kMaxTaps && NQ <= 4, "taps");
