@@ -1,6 +1,7 @@
 // fft.cu — host side of the fft.java replacement (jsdr_fft_* in jsdrcuda.h).
 #include <cstring>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -22,7 +23,16 @@ namespace fft {
 JSDR_FFT_PLANS(DECL)
 #undef DECL
 
+int launch_split_n8192(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st);
+int launch_split_n9600(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st);
+int launch_split_n16384(jsdr_ctx *ctx, const Args &a, int in_fmt, int out_mode, cudaStream_t st);
+
 typedef int (*launch_fn)(jsdr_ctx *, const Args &, int, int, cudaStream_t);
+// measured (profiles/r02_fft_split.txt): 32768 as 2 x 16384 beats the four-step pair (0.278 / 0.424
+// against 0.256 / 0.355 of peak for s16 / float input); 16384 as 2 x 8192 and 19200 as 2 x 9600 do
+// not beat their whole-block plans (the second read and conversion of every sample and the
+// strided stores cost what the second CTA per SM gains)
+static const char kDefaultSplit[] = "32768";
 struct PlanEntry { int n; launch_fn fn; };
 static const PlanEntry kPlans[] = {
 #define ROW(N, T, G, R0, R1, R2, R3) {N, launch_n##N},
@@ -37,6 +47,26 @@ static const PlanEntry *find_plan(int n)
     return nullptr;
 }
 
+
+// Lengths that run as a split plan: two CTAs per block, each an n/2-point plan behind one
+// radix-2 decimation-in-frequency step folded into its loads (fft_kernel, SPLIT = 2).
+// JSDR_FFT_SPLIT="19200,16384" overrides the default list, "0" turns it off (A/B measurements).
+static launch_fn split_plan(int n)
+{
+    static const char *env = getenv("JSDR_FFT_SPLIT");
+    const char *list = env ? env : kDefaultSplit;
+    char want[16];
+    snprintf(want, sizeof(want), "%d", n);
+    const char *hit = strstr(list, want);
+    const size_t len = strlen(want);
+    if (!hit || (hit != list && hit[-1] != ',') || (hit[len] != 0 && hit[len] != ',')) return nullptr;
+    switch (n) {
+    case 16384: return launch_split_n8192;
+    case 19200: return launch_split_n9600;
+    case 32768: return launch_split_n16384;
+    }
+    return nullptr;
+}
 
 // ---- lengths without a single-CTA plan: fft_generic.cuh stages + a PSD pass -------------
 __global__ void __launch_bounds__(256) k_generic_load(const void *__restrict__ in, float2 *__restrict__ out, long long total,
@@ -237,9 +267,19 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
     a.ic = ic;
     a.qc = qc;
     a.pf_dist = 0;
+    a.tw2 = nullptr;
+    a.best = nullptr;
+    a.cnt = nullptr;
     if (out_mode == OUT_SPECTRUM && in_fmt != IN_F32) {
         set_error("spectrum output needs float input");
         return JSDR_EINVAL;
+    }
+    if (f->split) {
+        a.nblocks = 2 * batch;                    // half blocks
+        a.tw2 = f->d_tw2;
+        a.best = f->d_best;
+        a.cnt = f->d_cnt;
+        return reinterpret_cast<launch_fn>(f->launch)(f->ctx, a, in_fmt, out_mode, st);
     }
     if (f->fs_n1) return launch_fourstep(f, a, in_fmt, out_mode, st);
     if (!f->launch) return launch_generic(f, a, in_fmt, out_mode, st);
@@ -253,7 +293,7 @@ using namespace jsdr;
 
 extern "C" int jsdr_fft_supported(int n)
 {
-    if (fft::find_plan(n)) return 1;                       // single-CTA plan
+    if (fft::find_plan(n) || fft::split_plan(n)) return 1; // single-CTA plan (whole or split)
     if (n == 32768 || n == 65536) return 3;                // four-step pair
     return n >= 2 && fftg::make_plan(n).nstages > 0 ? 2 : 0;   // staged path (slower)
 }
@@ -274,26 +314,39 @@ extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, js
     f->rate = rate;
     f->max_batch = max_batch;
     f->launch = p ? reinterpret_cast<void *>(p->fn) : nullptr;   // null: four-step or the staged path
-    f->fs_n1 = (!p && n == 32768) ? 128 : (!p && n == 65536) ? 256 : 0;
-    // twiddle table exp(-2*pi*i*t/n), computed in double, rounded once
-    std::vector<float2> tw(n);
-    for (int t = 0; t < n; t++) {
-        double ang = 2.0 * M_PI * (double)t / (double)n;
+    if (fft::launch_fn sp = fft::split_plan(n)) {
+        f->launch = reinterpret_cast<void *>(sp);
+        f->split = 2;
+    }
+    f->fs_n1 = (!f->launch && n == 32768) ? 128 : (!f->launch && n == 65536) ? 256 : 0;
+    // twiddle table exp(-2*pi*i*t/m) of the transform the plan runs (m = n, or n/2 for a split
+    // plan), computed in double, rounded once
+    const int m = f->split ? n / f->split : n;
+    std::vector<float2> tw(m);
+    for (int t = 0; t < m; t++) {
+        double ang = 2.0 * M_PI * (double)t / (double)m;
         tw[t] = make_float2((float)cos(ang), (float)-sin(ang));
     }
-    cudaError_t e = cudaMalloc(&f->d_tw, sizeof(float2) * n);
-    if (e != cudaSuccess) {
-        delete f;
-        set_error("cudaMalloc twiddles: %s", cudaGetErrorString(e));
-        return JSDR_ENOMEM;
+    cudaError_t e = cudaMalloc(&f->d_tw, sizeof(float2) * m);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_tw, tw.data(), sizeof(float2) * m, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && f->split) {                          // the radix-2 step's twiddles and the halves' meeting point
+        for (int t = 0; t < m; t++) {
+            double ang = 2.0 * M_PI * (double)t / (double)n;
+            tw[t] = make_float2((float)cos(ang), (float)-sin(ang));
+        }
+        e = cudaMalloc(&f->d_tw2, sizeof(float2) * m);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_tw2, tw.data(), sizeof(float2) * m, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_best, sizeof(unsigned long long) * (size_t)max_batch);
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_cnt, sizeof(unsigned) * (size_t)max_batch);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->d_best, 0, sizeof(unsigned long long) * (size_t)max_batch, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->d_cnt, 0, sizeof(unsigned) * (size_t)max_batch, ctx->stream);
     }
-    e = cudaMemcpyAsync(f->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(f->d_tw);
-        delete f;
-        set_error("twiddle upload: %s", cudaGetErrorString(e));
-        return JSDR_ECUDA;
+        set_error("jsdr_fft_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        jsdr_fft_destroy(f);
+        return e == cudaErrorMemoryAllocation ? JSDR_ENOMEM : JSDR_ECUDA;
     }
     *out = f;
     return JSDR_OK;
@@ -311,6 +364,8 @@ extern "C" int jsdr_fft_destroy(jsdr_fft *f)
     cudaFree(f->d_work[0]);
     cudaFree(f->d_work[1]);
     cudaFree(f->d_best);
+    cudaFree(f->d_tw2);
+    cudaFree(f->d_cnt);
     delete f;
     return JSDR_OK;
 }

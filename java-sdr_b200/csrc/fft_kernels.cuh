@@ -346,6 +346,10 @@ struct Args {
     float db_off;         // 10*log10(cf): psd = 10*log10(re^2+im^2) + db_off, one FFMA behind the logarithm
     int ic, qc;           // I/Q DC correction added with 16-bit wrap (s16 input)
     int pf_dist;          // CTAs resident on the device (0: no L2 prefetch), see fft_kernel
+    // split plans (SPLIT = 2, see fft_kernel): nblocks counts HALF blocks
+    const float2 *tw2;          // exp(-2*pi*i*c/(2N)), c in [0, N)
+    unsigned long long *best;   // [real blocks] packed (dB key, ~bin) of the halves seen so far; zero between launches
+    unsigned *cnt;              // [real blocks] halves that have reported; zero between launches
 };
 
 __device__ __forceinline__ unsigned ordered_key(float v)
@@ -444,9 +448,18 @@ __device__ __forceinline__ void middle_pass(float2 *sm, const float2 *__restrict
     }
 }
 
-template <class P, int IN, int OUT>
+// SPLIT = 2 ("split plan"): a block of 2N samples is transformed as two independent N-point
+// transforms, one CTA each, by one radix-2 decimation-in-frequency step folded into the loads of
+// pass 0: CTA h = 0 transforms x[n] + x[n+N] and owns the even bins, CTA h = 1 transforms
+// (x[n] - x[n+N]) * w_2N^n and owns the odd bins.  Lengths whose whole block fills an SM's shared
+// memory (one CTA per SM, every warp in step between barriers) then run two (or more) CTAs per
+// SM that drift apart.  The block maximum is combined through one 64-bit atomicMax per half
+// (dB key in the high word, complemented bin in the low one: first strict maximum as at
+// fft.java:208-211) and the half that reports last publishes peak Hz / dB (:214-224).
+template <class P, int IN, int OUT, int SPLIT = 1>
 __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 {
+    static_assert(SPLIT == 1 || (SPLIT == 2 && P::G == 1), "split plans take one half block per CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ unsigned s_max[P::G];
@@ -454,9 +467,10 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 
     const int tid = threadIdx.x;
     constexpr int N = P::N;
+    constexpr int NR = N * SPLIT;                 // length of the block in memory
     // persistent only where the register prefetch exists (s16 input: one register per sample);
     // float input keeps one CTA per block and the L2 prefetch (measured: 0.50 -> 0.61 at 16384)
-    constexpr bool PERSIST = P::PERSIST && IN == IN_S16;
+    constexpr bool PERSIST = P::PERSIST && IN == IN_S16 && SPLIT == 1;
     constexpr bool PREFETCH = PERSIST;
 
     // pass-0 samples of the next block (persistent plans, s16 input)
@@ -492,6 +506,8 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             const long nb = blk0 + (long)a.pf_dist * P::G;
             if (nb + P::G <= a.nblocks) {
                 constexpr size_t EL = (IN == IN_S16) ? 4 : 8;
+                // (split plans: half block nb is N contiguous samples too — the two CTAs of a block
+                // bring in one half each, and each of them then reads both)
                 const size_t lo = (reinterpret_cast<size_t>(a.in) + (size_t)nb * N * EL + 15) & ~(size_t)15;
                 const size_t hi = (reinterpret_cast<size_t>(a.in) + (size_t)(nb + P::G) * N * EL) & ~(size_t)15;
                 if (hi > lo)
@@ -532,7 +548,56 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             long blk = blk0 + g;
             if (blk >= a.nblocks) continue;
             float2 v[R0];
-            if constexpr (IN == IN_S16 && P::GROUP_IN) {
+            if constexpr (SPLIT == 2) {
+                // one radix-2 decimation-in-frequency step on the way in (see above), eight inputs of
+                // the butterfly at a time so that only 2 x 8 raw values are ever live beside v[]
+                const long rblk = blk >> 1;
+                const int h = (int)(blk & 1);
+                constexpr int CHK = (R0 % 8 == 0) ? 8 : (R0 % 5 == 0) ? 5 : (R0 % 4 == 0) ? 4 : 2;
+                // w_2N^(c + m*NB0) = w_2N^c * exp(-2*pi*i*m/(2*R0)): one table value, constant rotations
+                const float2 wc = h ? __ldg(a.tw2 + c) : make_float2(1.f, 0.f);
+                static_for<0, R0 / CHK>([&](auto kk) {
+                    constexpr int m0 = decltype(kk)::value * CHK;
+                    float2 va[CHK], vb[CHK];
+                    if constexpr (IN == IN_S16) {
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in) + rblk * NR + c;
+                        uint32_t wa[CHK], wb[CHK];
+#pragma unroll
+                        for (int i = 0; i < CHK; i++) {
+                            wa[i] = ldg_stream_u32(src + (m0 + i) * NB0);
+                            wb[i] = ldg_stream_u32(src + N + (m0 + i) * NB0);
+                        }
+                        if (a.ic | a.qc) {
+#pragma unroll
+                            for (int i = 0; i < CHK; i++) {
+                                wa[i] = (((wa[i] & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((wa[i] >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
+                                wb[i] = (((wb[i] & 0xffffu) + (unsigned)a.ic) & 0xffffu) | ((((wb[i] >> 16) + (unsigned)a.qc) & 0xffffu) << 16);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < CHK; i++) {
+                            va[i] = s16_bits_to_float<P::PACK_IN>(wa[i]);
+                            vb[i] = s16_bits_to_float<P::PACK_IN>(wb[i]);
+                        }
+                    } else {
+                        const float2 *src = reinterpret_cast<const float2 *>(a.in) + rblk * NR + c;
+#pragma unroll
+                        for (int i = 0; i < CHK; i++) {
+                            va[i] = ldg_stream_f2(src + (m0 + i) * NB0);
+                            vb[i] = ldg_stream_f2(src + N + (m0 + i) * NB0);
+                        }
+                    }
+                    if (h == 0) {
+#pragma unroll
+                        for (int i = 0; i < CHK; i++) v[m0 + i] = cadd(va[i], vb[i]);
+                    } else {
+                        static_for<0, CHK>([&](auto ii) {
+                            constexpr int i = decltype(ii)::value;
+                            v[m0 + i] = cmul(cmul_w<m0 + i, 2 * R0>(csub(va[i], vb[i])), wc);
+                        });
+                    }
+                });
+            } else if constexpr (IN == IN_S16 && P::GROUP_IN) {
                 uint32_t w[R0];
                 if constexpr (PREFETCH) {
 #pragma unroll
@@ -625,12 +690,15 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             float2 w1 = __ldg(a.tw + j);
             twiddle_powers<RL>(v, w1);
             Dft<RL>::run(v);
+            // where this (half) block's bin k goes: bin SPLIT*k + h of block blk / SPLIT
+            const long rblk = blk / SPLIT;
+            const int h = (int)(blk % SPLIT);
             if constexpr (OUT == OUT_SPECTRUM) {
-                float2 *spec = reinterpret_cast<float2 *>(a.out) + blk * N;
+                float2 *spec = reinterpret_cast<float2 *>(a.out) + rblk * NR + h;
 #pragma unroll
-                for (int q = 0; q < RL; q++) stg_stream_f2(spec + j + q * ML, v[q]);
+                for (int q = 0; q < RL; q++) stg_stream_f2(spec + SPLIT * (j + q * ML), v[q]);
             } else {
-                float *psd = a.out + blk * (long)(N + 2);
+                float *psd = a.out + rblk * (long)(NR + 2) + h;
 #pragma unroll
                 for (int q = 0; q < RL; q++) {
                     // fft.java:207 (re*re + im*im) * cf -> dB.  The scale is applied behind the logarithm
@@ -639,7 +707,7 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                     float pw = fmaf(v[q].x, v[q].x, v[q].y * v[q].y);
                     // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is accurate to ~1e-7 in log2
                     db[it][q] = fmaf(3.0102999566398120f, lg2_approx(pw), a.db_off);
-                    stg_stream_f32(psd + j + q * ML, db[it][q]);
+                    stg_stream_f32(psd + SPLIT * (j + q * ML), db[it][q]);
                     // only the running maximum here (FMNMX; NaN never wins, and neither does
                     // anything <= -Float.MAX_VALUE)
                     best = fmaxf(best, db[it][q]);
@@ -679,22 +747,43 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             const int wg = GROUP_SYNC ? tid / P::ML : tid;
             if ((GROUP_SYNC ? (tid % P::ML == 0) : (tid < P::G)) && blk0 + wg < a.nblocks) {
                 long blk = blk0 + wg;
-                float *psd = a.out + blk * (long)(N + 2);
                 unsigned key = s_max[wg];
                 int bin = (key != 0u) ? s_idx[wg] : -1;
-                float m = -3.4028234663852886e38f;
-                if (key != 0u) {
-                    unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
-                    m = __uint_as_float(u);
+                bool publish = true;
+                if constexpr (SPLIT == 2) {
+                    // this half's maximum joins the block's; the half that reports last publishes
+                    const long rblk = blk >> 1;
+                    const int h = (int)(blk & 1);
+                    const unsigned long long mine =
+                        key ? ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)(2 * bin + h)) : 0ull;
+                    if (mine) atomicMax(&a.best[rblk], mine);
+                    __threadfence();
+                    publish = atomicAdd(&a.cnt[rblk], 1u) == 1u;
+                    if (publish) {
+                        __threadfence();
+                        const unsigned long long both = atomicExch(&a.best[rblk], 0ull);   // (left zero for the next launch)
+                        a.cnt[rblk] = 0u;
+                        key = (unsigned)(both >> 32);
+                        bin = key ? (int)(0xffffffffu - (unsigned)both) : -1;
+                        blk = rblk;
+                    }
                 }
-                // fft.java:214-221 with p = 2*bin, dat.length = 2N, int32 wrap, trunc division
-                int p = (bin < 0) ? -1 : 2 * bin;
-                const int datlen = 2 * N;
-                if (p >= datlen / 2) p -= datlen;
-                p = (int)((unsigned)p * (unsigned)a.rate) / datlen;
-                psd[N] = (float)p;
-                psd[N + 1] = m;
-                if (a.peak_bin) a.peak_bin[blk] = bin;
+                if (publish) {
+                    float *psd = a.out + blk * (long)(NR + 2);
+                    float m = -3.4028234663852886e38f;
+                    if (key != 0u) {
+                        unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+                        m = __uint_as_float(u);
+                    }
+                    // fft.java:214-221 with p = 2*bin, dat.length = 2N, int32 wrap, trunc division
+                    int p = (bin < 0) ? -1 : 2 * bin;
+                    const int datlen = 2 * NR;
+                    if (p >= datlen / 2) p -= datlen;
+                    p = (int)((unsigned)p * (unsigned)a.rate) / datlen;
+                    psd[NR] = (float)p;
+                    psd[NR + 1] = m;
+                    if (a.peak_bin) a.peak_bin[blk] = bin;
+                }
             }
         }
     }

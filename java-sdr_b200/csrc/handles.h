@@ -16,6 +16,9 @@ struct jsdr_fft {
     float2 *d_work[2] = {nullptr, nullptr};   // workspace of the four-step / staged paths (no single-CTA plan)
     unsigned long long *d_best = nullptr;     // [max_batch] packed block maxima (four-step path)
     int fs_n1 = 0;                            // four-step factor N1 (128 or 256), 0 otherwise
+    int split = 0;                            // 2: split plan — two n/2-point transforms per block (fft_kernel SPLIT)
+    float2 *d_tw2 = nullptr;                  // split plan: exp(-2*pi*i*c/n), c in [0, n/2)
+    unsigned *d_cnt = nullptr;                // split plan: halves reported per block (zero between launches)
     // staging for host-pointer calls (allocated on first use)
     void *d_in = nullptr;
     float *d_out = nullptr;

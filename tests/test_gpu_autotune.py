@@ -66,7 +66,8 @@ def test_autotune_needs_whole_blocks(ctx):
 def test_fft_staged_path_lengths_without_a_single_cta_plan(ctx, n):
     """BASELINE config 3's sweep tops out at 65536: those lengths (and any other
     2,3,5,7-smooth length) run through the staged Stockham path."""
-    assert J.lib().jsdr_fft_supported(n) == (3 if n in (32768, 65536) else 2)
+    # 65536: the four-step pair; 32768: a split plan (two 16384-point CTAs per block); else staged
+    assert J.lib().jsdr_fft_supported(n) == {65536: 3, 32768: 1}.get(n, 2)
     rng = np.random.default_rng(n)
     batch = 5
     x = rng.uniform(-1, 1, (batch, 2 * n)).astype(np.float32)
