@@ -2,8 +2,8 @@
  * jsdr_oracle.c — CPU restatement of java-sdr's IQ front-end arithmetic.
  *
  * TEST INFRASTRUCTURE ONLY — see jsdr_oracle.h for the rules and for the
- * parity status ("PARITY UNPINNED" for the FFT; the rest pinned only by the
- * sync-LFSR identity and the FEC round trip).
+ * parity status (tables, taps and constants pinned to every literal of the
+ * reference; "PARITY UNPINNED" for the FFT, whose arithmetic is JTransforms').
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -pthread
  * (-ffp-contract=off because Java never fuses a*b+c).

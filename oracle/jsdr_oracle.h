@@ -6,19 +6,27 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / reported CPU baseline.
  *
- * PARITY STATUS
+ * PARITY STATUS (what pins this restatement to the reference)
+ *   - PINNED to reference data, every entry (tests/test_ref_tables.py against
+ *     tests/golden/ref_tables.npz, parsed from the Java sources by
+ *     tests/golden/make_ref_tables.py): Partab, mettab, Syms, Scrambler,
+ *     ALPHA_TO / INDEX_OF, RS_poly (FECDecoder.java:40-181,544-546), the
+ *     decimator and matched-filter taps and SYNC_VECTOR
+ *     (FUNcubeBPSKDemod.java:27-81) and the scalar constants — the literal
+ *     tables ARE the reference's golden data.  On top of them: the
+ *     sync-LFSR (FECDecoder.java:600-605) == SYNC_VECTOR identity and the
+ *     encode -> modulate -> demodulate -> FECDecode round trip.
+ *   - FIR / NCO / tuner / decimator / matched filter / bit timing / FEC:
+ *     a line by line restatement in Java numeric semantics (strict IEEE, no
+ *     FMA contraction, float-literal taps widened, (int) saturating casts).
+ *     The reference ships no tests or golden OUTPUTS and no JVM exists
+ *     here, so outputs are pinned through the tables above, the identities
+ *     and first-principles known answers, not through recorded reference runs.
  *   - FFT (fft.java:194-195, FUNcubeBPSKDemod.java:422-423,459): the
  *     arithmetic lives in JTransforms 2.4 (reference Makefile:8), which is
  *     absent from /root/reference.  The oracle is the mathematical DFT in
- *     binary64.  PARITY UNPINNED by any reference artefact.
- *   - FIR / NCO / tuner / decimator / matched filter / bit timing: a line
- *     by line restatement in Java numeric semantics (strict IEEE, no FMA
- *     contraction, float-literal taps widened, (int) saturating casts).
- *     The reference ships no tests or golden vectors and no JVM exists
- *     here, so these are pinned only by (i) the reference-anchored
- *     identity sync-LFSR (FECDecoder.java:600-605) == SYNC_VECTOR
- *     (FUNcubeBPSKDemod.java:79-81) and (ii) the encode -> modulate ->
- *     demodulate -> FECDecode round trip.  Otherwise PARITY UNPINNED.
+ *     binary64.  PARITY UNPINNED by any reference artefact (stated as the
+ *     task requires); Java's Math.sin/cos/log10 likewise (<= 1 ulp, not run).
  *
  * All file:line citations are relative to the reference checkout.
  */
