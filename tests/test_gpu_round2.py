@@ -209,3 +209,22 @@ def test_period_ring_kernel_bit_exact(ctx, ntaps):
             assert np.array_equal(out[J.KERNEL_PRING][c], o.receive(O.s16_to_float(raw[c]))["ds"]), (S, c)
     for b in banks.values():
         b.close()
+
+
+def test_pump_waterfall_argument_errors(ctx):
+    """Bad arguments are refused with a status code (nothing throws across the ABI)."""
+    adsc = J.AudioDescriptor(96000)
+    f = J.fft(ctx, None, adsc, max_batch=8, n=256)
+    b = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0] * 4, max_block=512, stages=1)
+    raw = np.zeros((4, 2 * 512), np.int16)
+    pix = np.zeros((8, 300), np.int32)
+    peak = np.zeros((8, 2), np.float32)
+    with pytest.raises(J.JsdrError):
+        J.pump_waterfall_s16(f, b, raw, 2, 300, pix, peak)          # width > n
+    with pytest.raises(J.JsdrError):
+        J.pump_waterfall_s16(f, b, raw, 3, 64, pix, peak)           # nblocks*n beyond the bank's block / the fft's batch
+    pix = np.zeros((8, 64), np.int32)
+    J.pump_waterfall_s16(f, b, raw, 2, 64, pix, peak)               # and the good call still works afterwards
+    assert np.all(np.isneginf(peak[:, 1]) | (peak[:, 1] < -300))    # silence: no bin ever compared greater
+    f.close()
+    b.close()
