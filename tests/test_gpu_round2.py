@@ -118,7 +118,9 @@ def test_pump_applies_iq_correction(ctx):
     f = J.fft(ctx, None, adsc, max_batch=nch * nblk, n=n)
     bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tun, max_block=n * nblk, stages=1)
     psd = np.empty((nch * nblk, n + 2), np.float32)
+    before = raw.copy()
     J.pump_receive_s16(f, bank, raw, nblk, psd, ic=ic, qc=qc)
+    assert np.array_equal(raw, before)                   # raw handlers (recorder.java:66) see uncorrected bytes
     ds = bank.read_ds()
     for c in (0, 17, 39):
         o = O.Bpsk(rate, tun[c], stages=1)
