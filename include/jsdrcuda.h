@@ -46,7 +46,8 @@ typedef enum jsdr_status {
     JSDR_ECUDA = -2,        /* CUDA runtime error / no device */
     JSDR_ENOMEM = -3,
     JSDR_EUNSUPPORTED = -4, /* e.g. an FFT length with no plan */
-    JSDR_ESTATE = -5        /* call out of order */
+    JSDR_ESTATE = -5,       /* call out of order */
+    JSDR_EINTERNAL = -6     /* a C++ exception other than out-of-memory was caught at the boundary */
 } jsdr_status;
 
 enum { JSDR_MEM_HOST = 0, JSDR_MEM_DEVICE = 1 };

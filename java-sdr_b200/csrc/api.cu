@@ -28,17 +28,17 @@ extern "C" int jsdr_abi_version(void) { return JSDR_ABI_VERSION; }
 extern "C" const char *jsdr_last_error(void) { return g_err; }
 
 extern "C" int jsdr_device_count(int *count)
-{
+try {
     JSDR_REQUIRE(count, JSDR_EINVAL, "null argument");
     *count = 0;
     JSDR_CUDA(cudaGetDeviceCount(count));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 static int ctx_init(jsdr_ctx *ctx);
 
 extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
-{
+try {
     JSDR_REQUIRE(out, JSDR_EINVAL, "null argument");
     *out = nullptr;
     int count = 0;
@@ -67,7 +67,7 @@ extern "C" int jsdr_ctx_create(int device, jsdr_ctx **out)
     }
     *out = ctx;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 static int ctx_init(jsdr_ctx *ctx)
 {
@@ -100,7 +100,7 @@ static int ctx_init(jsdr_ctx *ctx)
 }
 
 extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
-{
+try {
     if (!ctx) return JSDR_OK;
     ctx->bind();
     cudaStream_t *streams[] = {&ctx->stream, &ctx->side, &ctx->side2, &ctx->aux, &ctx->copy_in, &ctx->copy_out};
@@ -123,10 +123,10 @@ extern "C" int jsdr_ctx_destroy(jsdr_ctx *ctx)
     cudaGetLastError();
     delete ctx;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
-{
+try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaStreamSynchronize(ctx->side));
@@ -135,25 +135,25 @@ extern "C" int jsdr_ctx_sync(jsdr_ctx *ctx)
     JSDR_CUDA(cudaStreamSynchronize(ctx->copy_out));
     JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count)
-{
+try {
     JSDR_REQUIRE(ctx && count, JSDR_EINVAL, "null argument");
     *count = ctx->launches;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_ctx_profile(jsdr_ctx *ctx, int enable)
-{
+try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     ctx->profiling = enable != 0;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // Sum the event-bracketed durations recorded since the last read, per kernel kind.
 extern "C" int jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, int nkinds)
-{
+try {
     JSDR_REQUIRE(ctx && ms && count && nkinds >= JSDR_K_COUNT, JSDR_EINVAL, "need room for JSDR_K_COUNT kinds");
     JSDR_TRY(ctx->bind());
     JSDR_TRY(jsdr_ctx_sync(ctx));                   // spans are recorded on every compute stream (bit timing: aux)
@@ -177,26 +177,26 @@ extern "C" int jsdr_ctx_profile_read(jsdr_ctx *ctx, double *ms, int64_t *count, 
     }
     ctx->spans.clear();
     return rc;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_host_alloc(jsdr_ctx *ctx, size_t bytes, void **out)
-{
+try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_host_free(jsdr_ctx *ctx, void *p)
-{
+try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     if (p) JSDR_CUDA(cudaFreeHost(p));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_dev_alloc(jsdr_ctx *ctx, size_t bytes, void **out)
-{
+try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
@@ -206,52 +206,52 @@ extern "C" int jsdr_dev_alloc(jsdr_ctx *ctx, size_t bytes, void **out)
         return e == cudaErrorMemoryAllocation ? JSDR_ENOMEM : JSDR_ECUDA;
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_dev_free(jsdr_ctx *ctx, void *p)
-{
+try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     if (p) JSDR_CUDA(cudaFree(p));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_memcpy_h2d(jsdr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
-{
+try {
     JSDR_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_memcpy_d2h(jsdr_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
-{
+try {
     JSDR_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_memset_dev(jsdr_ctx *ctx, void *dst_dev, int value, size_t bytes)
-{
+try {
     JSDR_REQUIRE(ctx && dst_dev, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_timer_start(jsdr_ctx *ctx)
-{
+try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     JSDR_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_timer_stop_ms(jsdr_ctx *ctx, float *ms)
-{
+try {
     JSDR_REQUIRE(ctx && ms, JSDR_EINVAL, "null argument");
     JSDR_TRY(ctx->bind());
     // the timed region ends when the auxiliary stream (bit timing, frames) is done as well; the side
@@ -262,4 +262,4 @@ extern "C" int jsdr_timer_stop_ms(jsdr_ctx *ctx, float *ms)
     JSDR_CUDA(cudaEventSynchronize(ctx->ev_t1));
     JSDR_CUDA(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL

@@ -1445,7 +1445,7 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
 
 extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double *tuning_hz,
                                 int max_block_samples, jsdr_bpsk **out)
-{
+try {
     JSDR_REQUIRE(ctx && out && tuning_hz, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(rate >= 9600 && rate <= 64 * 9600 && nchan > 0 && nchan <= 65535 && max_block_samples > 0,
                  JSDR_EINVAL, "need 9600 <= rate <= 614400, 0 < nchan < 65536, max_block_samples > 0");
@@ -1540,10 +1540,10 @@ extern "C" int jsdr_bpsk_create(jsdr_ctx *ctx, int rate, int nchan, const double
     }
     *out = b;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
-{
+try {
     if (!b) return JSDR_OK;
     b->ctx->bind();
     cudaStreamSynchronize(b->ctx->side);
@@ -1569,25 +1569,25 @@ extern "C" int jsdr_bpsk_destroy(jsdr_bpsk *b)
     }
     delete b;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_stages(jsdr_bpsk *b, int stages)
-{
+try {
     JSDR_REQUIRE(b && stages >= 1 && stages <= 3, JSDR_EINVAL, "stages must be 1..3");
     b->stages = stages;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_autotune(jsdr_bpsk *b, int dofft, int do_upper)
-{
+try {
     JSDR_REQUIRE(b, JSDR_EINVAL, "null argument");
     b->dofft = dofft != 0;
     b->doUp = do_upper != 0;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_read_centre(jsdr_bpsk *b, int32_t *centre_bin)
-{
+try {
     JSDR_REQUIRE(b && centre_bin, JSDR_EINVAL, "null argument");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
@@ -1598,24 +1598,24 @@ extern "C" int jsdr_bpsk_read_centre(jsdr_bpsk *b, int32_t *centre_bin)
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int c = 0; c < b->nchan; c++) centre_bin[c] = st[c].centreBin;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_precision(jsdr_bpsk *b, int precision)
-{
+try {
     JSDR_REQUIRE(b && (precision == JSDR_PREC_F64 || precision == JSDR_PREC_F32), JSDR_EINVAL, "bad precision");
     b->precision = precision;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_kernel(jsdr_bpsk *b, int mode)
-{
+try {
     JSDR_REQUIRE(b && mode >= JSDR_KERNEL_AUTO && mode <= JSDR_KERNEL_PRING, JSDR_EINVAL, "bad kernel mode");
     b->kernel_mode = mode;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
-{
+try {
     JSDR_REQUIRE(b && chan >= 0 && chan < b->nchan, JSDR_EINVAL, "bad channel");
     JSDR_TRY(b->ctx->bind());
     // the scout may be running ahead with the old increment: let it finish and drop its plan
@@ -1631,10 +1631,10 @@ extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
     const ScoutChan sc = scout_chan(inc);
     JSDR_TRY(upload(b->ctx, b->d_tu_par + chan, &sc, sizeof(sc)));
     return upload(b->ctx, b->d_tu_inc + chan, &inc, sizeof(double));
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_set_ds_filter(jsdr_bpsk *b, const double *taps, int ntaps)
-{
+try {
     JSDR_REQUIRE(b && taps && ntaps >= 1 && ntaps <= kMaxDsTaps, JSDR_EINVAL, "1..128 taps");
     JSDR_TRY(b->ctx->bind());
     std::vector<double> t(kMaxDsTaps, 0.0);
@@ -1643,25 +1643,25 @@ extern "C" int jsdr_bpsk_set_ds_filter(jsdr_bpsk *b, const double *taps, int nta
     for (int i = 0; i < kMaxDsTaps; i++) b->h_taps[i] = t[i];
     b->ntaps = ntaps;
     return bpsk_reset_ds(b);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_receive_f32(jsdr_bpsk *b, const float *iq, int nsamples, int64_t chan_stride, int mem)
-{
+try {
     return bpsk_receive<FMT_F32>(b, iq, nsamples, chan_stride, 0, 0, mem);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_receive_s16(jsdr_bpsk *b, const int16_t *raw, int nsamples, int64_t chan_stride,
                                      int ic, int qc, int mem)
-{
+try {
     return bpsk_receive<FMT_S16>(b, raw, nsamples, chan_stride, ic, qc, mem);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_last_counts(jsdr_bpsk *b, int32_t *n_ds)
-{
+try {
     JSDR_REQUIRE(b && n_ds, JSDR_EINVAL, "null argument");
     *n_ds = b->last_nds;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 namespace {
 int read_rows(jsdr_bpsk *b, const double2 *src, double *out, int mem)
@@ -1685,7 +1685,7 @@ extern "C" int jsdr_bpsk_read_ds(jsdr_bpsk *b, double *out, int mem) { return re
 // copy overlaps whatever the caller submits next (the upload of the following block, in the
 // pump); jsdr_ctx_sync -- or the next synchronous read -- completes it.
 extern "C" int jsdr_bpsk_read_ds_async(jsdr_bpsk *b, double *out, int mem)
-{
+try {
     JSDR_REQUIRE(b && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
     jsdr_ctx *ctx = b->ctx;
@@ -1704,17 +1704,17 @@ extern "C" int jsdr_bpsk_read_ds_async(jsdr_bpsk *b, double *out, int mem)
     JSDR_CUDA(cudaEventRecord(b->ev_ds_read, ctx->copy_out));
     b->ds_read_pending = 1;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_read_dm(jsdr_bpsk *b, double *out, int mem)
-{
+try {
     JSDR_REQUIRE(b && b->stages >= 2 && b->d_dm_out, JSDR_ESTATE, "matched filter stage is disabled or has not run");
     return read_rows(b, b->d_dm_out, out, mem);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_read_bits(jsdr_bpsk *b, int8_t *bits, int64_t *bit_at, int32_t *nbits,
                                    int max_bits, int mem)
-{
+try {
     JSDR_REQUIRE(b && nbits, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(b->stages >= 3 && b->d_bits, JSDR_ESTATE, "bit decision stage is disabled or has not run");
     JSDR_REQUIRE(max_bits >= 0, JSDR_EINVAL, "negative max_bits");
@@ -1732,10 +1732,10 @@ extern "C" int jsdr_bpsk_read_bits(jsdr_bpsk *b, int8_t *bits, int64_t *bit_at, 
                                     ctx->aux));
     if (mem == JSDR_MEM_HOST) JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_read_counters(jsdr_bpsk *b, int64_t *counters)
-{
+try {
     JSDR_REQUIRE(b && counters, JSDR_EINVAL, "null argument");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
@@ -1750,14 +1750,14 @@ extern "C" int jsdr_bpsk_read_counters(jsdr_bpsk *b, int64_t *counters)
         counters[4 * c + 3] = 0;
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_ds_device_ptr(jsdr_bpsk *b, double **dev_ptr)
-{
+try {
     JSDR_REQUIRE(b && dev_ptr, JSDR_EINVAL, "null argument");
     *dev_ptr = reinterpret_cast<double *>(b->d_ds_out);
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // ------------------------------------------------------------------ the pump
 namespace {
@@ -1800,10 +1800,10 @@ int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int
 
 extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks,
                                      int ic, int qc, float *psd, int32_t *peak_bin, int mem)
-{
+try {
     JSDR_REQUIRE(psd, JSDR_EINVAL, "null argument");
     return pump_receive(f, b, raw, nblocks, ic, qc, psd, peak_bin, mem, nullptr);
-}
+} JSDR_CATCH_ALL
 
 // The same fan-out with waterfall.java's paintLine (:90-107) chained behind every block's PSD on
 // the device: what returns is the pixel row a waterfall draws and the two published maxima
@@ -1811,12 +1811,12 @@ extern "C" int jsdr_pump_receive_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *r
 extern "C" int jsdr_pump_waterfall_s16(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc,
                                        int width, uint32_t peak_rgb, int32_t *pixels, float *peak, int32_t *peak_bin,
                                        int mem)
-{
+try {
     JSDR_REQUIRE(f && pixels && peak, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(width > 0 && width <= f->n, JSDR_EINVAL, "need 0 < width <= n");
     PumpPixels px = {width, peak_rgb, pixels, peak};
     return pump_receive(f, b, raw, nblocks, ic, qc, nullptr, peak_bin, mem, &px);
-}
+} JSDR_CATCH_ALL
 
 namespace {
 int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int ic, int qc, float *psd,
@@ -1932,20 +1932,20 @@ int pump_receive(jsdr_fft *f, jsdr_bpsk *b, const int16_t *raw, int nblocks, int
 // (tests/test_ref_tables.py compares every entry with the literals parsed from the Java source).
 // Host only: no device needed.
 extern "C" int jsdr_probe_taps(double *ds27, double *dm65)
-{
+try {
     JSDR_REQUIRE(ds27 && dm65, JSDR_EINVAL, "null argument");
     for (int i = 0; i < 27; i++) ds27[i] = (double)jsdr::bpsk::kDsFilterF[i];
     for (int i = 0; i < 65; i++) dm65[i] = (double)jsdr::bpsk::kDmFilterF[i];
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // The exact wrap thresholds the phase scout uses for one tuner increment (scout_thresholds):
 // host only, for tests/test_scout_thresholds.py, which checks on the CPU that `p > th1` / `p > th2`
 // ARE the reference's comparisons (FUNcubeBPSKDemod.java:385) for every double around them.
 extern "C" int jsdr_probe_scout_thresholds(double inc, double *th1, double *th2)
-{
+try {
     JSDR_REQUIRE(th1 && th2, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(inc > 0.0 && inc < 3.1, JSDR_EINVAL, "the pair form covers 0 < inc < 3.1");
     scout_thresholds(inc, *th1, *th2);
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -37,6 +39,26 @@ void set_error(const char *fmt, ...);
         int _rc = (expr);                                                            \
         if (_rc != JSDR_OK) return _rc;                                              \
     } while (0)
+
+// Every entry point is a function-try-block closed by this: the header promises that nothing
+// throws across the C boundary (a C++ exception unwinding into a JVM frame ends the process), so a
+// failed host allocation (new, std::vector) comes back as a status like every other failure.
+#define JSDR_CATCH_ALL                                                               \
+    catch (const std::bad_alloc &)                                                   \
+    {                                                                                \
+        jsdr::set_error("%s: out of host memory", __func__);                         \
+        return JSDR_ENOMEM;                                                          \
+    }                                                                                \
+    catch (const std::exception &e_)                                                 \
+    {                                                                                \
+        jsdr::set_error("%s: %s", __func__, e_.what());                              \
+        return JSDR_EINTERNAL;                                                       \
+    }                                                                                \
+    catch (...)                                                                      \
+    {                                                                                \
+        jsdr::set_error("%s: unknown C++ exception", __func__);                      \
+        return JSDR_EINTERNAL;                                                       \
+    }
 
 }  // namespace jsdr
 

@@ -222,7 +222,7 @@ int grow(void **p, size_t *cap, size_t bytes)
 
 // =========================================================================== demod
 extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_block_samples, jsdr_demod **out)
-{
+try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(rate > 0 && nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
     JSDR_TRY(ctx->bind());
@@ -258,10 +258,10 @@ extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_blo
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = d;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_demod_destroy(jsdr_demod *d)
-{
+try {
     if (!d) return JSDR_OK;
     d->ctx->bind();
     cudaStreamSynchronize(d->ctx->side);
@@ -271,11 +271,11 @@ extern "C" int jsdr_demod_destroy(jsdr_demod *d)
     for (void *p : ptrs) cudaFree(p);
     delete d;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // demod.weights(), demod.java:341-375
 extern "C" int jsdr_demod_weights(jsdr_demod *d, int chan, int flo, int fhi)
-{
+try {
     JSDR_REQUIRE(d && chan >= 0 && chan < d->nchan, JSDR_EINVAL, "bad channel");
     jsdr_ctx *ctx = d->ctx;
     JSDR_TRY(ctx->bind());
@@ -308,22 +308,22 @@ extern "C" int jsdr_demod_weights(jsdr_demod *d, int chan, int flo, int fhi)
         JSDR_CUDA(cudaMemsetAsync(d->d_hist[i] + (size_t)chan * kHist, 0, sizeof(float2) * kHist, ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_demod_get_weights(jsdr_demod *d, int chan, float w[21])
-{
+try {
     JSDR_REQUIRE(d && w && chan >= 0 && chan < d->nchan, JSDR_EINVAL, "bad channel");
     memcpy(w, &d->h_w[(size_t)chan * kTaps], sizeof(float) * kTaps);
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_demod_set_flags(jsdr_demod *d, int dofir, int dodwn)
-{
+try {
     JSDR_REQUIRE(d, JSDR_EINVAL, "null argument");
     d->dofir = dofir != 0;
     d->dodwn = dodwn != 0;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 namespace {
 
@@ -395,7 +395,7 @@ int demod_check(jsdr_demod *d, const void *iq, const void *out, int S, int64_t c
 
 extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
                                       float *out, int mem)
-{
+try {
     JSDR_TRY(demod_check(d, iq, out, S, chan_stride, mem));
     if (S == 0) return JSDR_OK;
     jsdr_ctx *ctx = d->ctx;
@@ -407,7 +407,7 @@ extern "C" int jsdr_demod_receive_f32(jsdr_demod *d, const float *iq, int S, int
         JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // ------------------------------------------------------------------ detectors, AGC, s16 (:405-481)
 namespace jsdr {
@@ -520,16 +520,16 @@ __global__ void __launch_bounds__(256) k_detect(const float2 *__restrict__ mixed
 }  // namespace jsdr
 
 extern "C" int jsdr_demod_set_mode(jsdr_demod *d, int mode, int doagc)
-{
+try {
     JSDR_REQUIRE(d && mode >= dsp::MODE_OFF && mode <= dsp::MODE_WFM, JSDR_EINVAL, "mode must be 0..4 (demod.java:39-43)");
     d->mode = mode;
     d->doagc = doagc != 0;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_demod_receive_audio_f32(jsdr_demod *d, const float *iq, int S, int64_t chan_stride,
                                             int16_t *audio, float *max_avg, int mem)
-{
+try {
     JSDR_TRY(demod_check(d, iq, audio, S, chan_stride, mem));
     if (S == 0) return JSDR_OK;
     jsdr_ctx *ctx = d->ctx;
@@ -560,12 +560,12 @@ extern "C" int jsdr_demod_receive_audio_f32(jsdr_demod *d, const float *iq, int 
         JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // =========================================================================== fir.java
 // fir.weights(), fir.java:169-195 (host, one-off)
 extern "C" int jsdr_fir_design(int f1, int f2, float rate, double w[21])
-{
+try {
     JSDR_REQUIRE(w && rate > 0, JSDR_EINVAL, "bad argument");
     if (f1 == INT_MIN && f2 == INT_MIN) {
         for (int i = 0; i < kTaps; i++) w[i] = 0;
@@ -585,11 +585,11 @@ extern "C" int jsdr_fir_design(int f1, int f2, float rate, double w[21])
         w[n] = w[n] * (0.54 - 0.46 * cos(2 * M_PI * n / ord));
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // one period of complex_gen, fir.java:221-228 (the counter wraps at (int)rate)
 extern "C" int jsdr_fir_nco_table(int freq, float rate, int32_t *sig)
-{
+try {
     JSDR_REQUIRE(sig && rate >= 1.0f, JSDR_EINVAL, "bad argument");
     const int period = (int)rate;
     for (int n = 0; n < period; n++) {
@@ -598,10 +598,10 @@ extern "C" int jsdr_fir_nco_table(int freq, float rate, int32_t *sig)
         sig[2 * n + 1] = java_d2i(sin(w) * 4096);
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fir_create(jsdr_ctx *ctx, int nchan, int max_block_samples, jsdr_fir **out)
-{
+try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
     JSDR_TRY(ctx->bind());
@@ -625,10 +625,10 @@ extern "C" int jsdr_fir_create(jsdr_ctx *ctx, int nchan, int max_block_samples, 
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = f;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fir_destroy(jsdr_fir *f)
-{
+try {
     if (!f) return JSDR_OK;
     f->ctx->bind();
     cudaStreamSynchronize(f->ctx->stream);
@@ -636,10 +636,10 @@ extern "C" int jsdr_fir_destroy(jsdr_fir *f)
     for (void *p : ptrs) cudaFree(p);
     delete f;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fir_set_weights(jsdr_fir *f, int chan, const double w[21])
-{
+try {
     JSDR_REQUIRE(f && w && chan >= 0 && chan < f->nchan, JSDR_EINVAL, "bad channel");
     jsdr_ctx *ctx = f->ctx;
     JSDR_TRY(ctx->bind());
@@ -648,11 +648,11 @@ extern "C" int jsdr_fir_set_weights(jsdr_fir *f, int chan, const double w[21])
         JSDR_CUDA(cudaMemsetAsync(f->d_hist[i] + (size_t)chan * kHist, 0, sizeof(int32_t) * kHist, ctx->stream));
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fir_filter_i32(jsdr_fir *f, const int32_t *in, int S, int64_t chan_stride,
                                    int32_t *out, int mem)
-{
+try {
     JSDR_REQUIRE(f && in && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(S >= 0 && S <= f->max_block, JSDR_EINVAL, "nsamples exceeds max_block_samples");
     JSDR_REQUIRE(chan_stride == 0 || chan_stride >= S, JSDR_EINVAL, "chan_stride smaller than nsamples");
@@ -694,11 +694,11 @@ extern "C" int jsdr_fir_filter_i32(jsdr_fir *f, const int32_t *in, int S, int64_
         JSDR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const int32_t *b, int32_t *out,
                                         int64_t npairs, int mem)
-{
+try {
     JSDR_REQUIRE(ctx && a && b && out && npairs >= 0, JSDR_EINVAL, "bad argument");
     JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
     if (npairs == 0) return JSDR_OK;
@@ -726,7 +726,7 @@ extern "C" int jsdr_fir_complex_mod_i32(jsdr_ctx *ctx, const int32_t *a, const i
         cudaFree(tmp);
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // =========================================================================== waterfall.java
 // paintLine (waterfall.java:90-107): max-decimate one published "fft-psd" row to the pixel
@@ -770,7 +770,7 @@ int jsdr_launch_waterfall(jsdr_ctx *ctx, const float *d_psd, int n, int rows, in
 
 extern "C" int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int rows, int width, uint32_t peak_rgb,
                                    int32_t *pixels, int mem)
-{
+try {
     JSDR_REQUIRE(ctx && psd && pixels, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(n > 0 && rows >= 0 && width > 0 && width <= n, JSDR_EINVAL, "need 0 < width <= n");
     JSDR_REQUIRE(mem == JSDR_MEM_HOST || mem == JSDR_MEM_DEVICE, JSDR_EINVAL, "bad mem");
@@ -804,4 +804,4 @@ extern "C" int jsdr_waterfall_rows(jsdr_ctx *ctx, const float *psd, int n, int r
         }
     }
     return rc;
-}
+} JSDR_CATCH_ALL

@@ -475,7 +475,7 @@ struct jsdr_fec_state {
 };
 
 extern "C" int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max_frames)
-{
+try {
     JSDR_REQUIRE(b && mettab && max_frames > 0, JSDR_EINVAL, "bad argument");
     jsdr_ctx *ctx = b->ctx;
     JSDR_TRY(ctx->bind());
@@ -523,7 +523,7 @@ extern "C" int jsdr_bpsk_enable_fec(jsdr_bpsk *b, const int16_t *mettab, int max
     JSDR_CUDA(cudaStreamSynchronize(ctx->stream));            // the stage itself runs on the auxiliary stream
     b->fec = f;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // called by bpsk_receive after the bit-timing stage; like that stage it runs on the auxiliary stream
 int jsdr_fec_after_bits(jsdr_bpsk *b)
@@ -573,7 +573,7 @@ void jsdr_fec_destroy(jsdr_bpsk *b)
 
 extern "C" int jsdr_bpsk_read_frames(jsdr_bpsk *b, int32_t *nframes, int32_t *chan, int64_t *bit_index,
                                      int32_t *errors, uint8_t *data, int max_frames)
-{
+try {
     JSDR_REQUIRE(b && nframes, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(b->fec, JSDR_ESTATE, "jsdr_bpsk_enable_fec has not been called");
     jsdr_fec_state *f = b->fec;
@@ -607,10 +607,10 @@ extern "C" int jsdr_bpsk_read_frames(jsdr_bpsk *b, int32_t *nframes, int32_t *ch
     }
     *nframes = n;                                               // detections this call (may exceed what fitted)
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_bpsk_read_fec_counters(jsdr_bpsk *b, int64_t *cnt_fec, int64_t *cnt_dec)
-{
+try {
     JSDR_REQUIRE(b && cnt_fec && cnt_dec, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(b->fec, JSDR_ESTATE, "jsdr_bpsk_enable_fec has not been called");
     jsdr_ctx *ctx = b->ctx;
@@ -620,13 +620,13 @@ extern "C" int jsdr_bpsk_read_fec_counters(jsdr_bpsk *b, int64_t *cnt_fec, int64
     JSDR_CUDA(cudaMemcpyAsync(cnt_dec, b->fec->d_cnt + nc, sizeof(long long) * nc, cudaMemcpyDeviceToHost, ctx->aux));
     JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 // ---- the tables this library builds for itself, for the reference-pinning tests (host only, no
 // device needed): tests/test_ref_tables.py compares every entry with the literals of
 // FECDecoder.java:40-57,105-181,544-546 and FUNcubeBPSKDemod.java:79-81.
 extern "C" int jsdr_probe_table(int which, int32_t *out, int n)
-{
+try {
     JSDR_REQUIRE(out && n >= 0, JSDR_EINVAL, "null argument");
     fec::Tables t;
     fec::build_tables(t);
@@ -644,4 +644,4 @@ extern "C" int jsdr_probe_table(int which, int32_t *out, int n)
         }
     }
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL

@@ -292,14 +292,14 @@ int launch(jsdr_fft *f, const void *d_in, int in_fmt, int batch, float *d_out, i
 using namespace jsdr;
 
 extern "C" int jsdr_fft_supported(int n)
-{
+try {
     if (fft::find_plan(n) || fft::split_plan(n)) return 1; // single-CTA plan (whole or split)
     if (n == 32768 || n == 65536) return 3;                // four-step pair
     return n >= 2 && fftg::make_plan(n).nstages > 0 ? 2 : 0;   // staged path (slower)
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, jsdr_fft **out)
-{
+try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(max_batch > 0 && rate > 0, JSDR_EINVAL, "max_batch and rate must be positive");
     const fft::PlanEntry *p = fft::find_plan(n);
@@ -350,10 +350,10 @@ extern "C" int jsdr_fft_create(jsdr_ctx *ctx, int n, int rate, int max_batch, js
     }
     *out = f;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fft_destroy(jsdr_fft *f)
-{
+try {
     if (!f) return JSDR_OK;
     f->ctx->bind();
     cudaFree(f->d_tw);
@@ -368,7 +368,7 @@ extern "C" int jsdr_fft_destroy(jsdr_fft *f)
     cudaFree(f->d_cnt);
     delete f;
     return JSDR_OK;
-}
+} JSDR_CATCH_ALL
 
 namespace {
 
@@ -423,17 +423,17 @@ int fft_run(jsdr_fft *f, const void *in, int in_fmt, int batch, int ic, int qc, 
 
 extern "C" int jsdr_fft_receive_f32(jsdr_fft *f, const float *iq, int batch, float *psd,
                                     int32_t *peak_bin, int mem)
-{
+try {
     return fft_run(f, iq, fft::IN_F32, batch, 0, 0, psd, peak_bin, fft::OUT_PSD, mem);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fft_receive_s16(jsdr_fft *f, const int16_t *raw, int batch, int ic, int qc,
                                     float *psd, int32_t *peak_bin, int mem)
-{
+try {
     return fft_run(f, raw, fft::IN_S16, batch, ic, qc, psd, peak_bin, fft::OUT_PSD, mem);
-}
+} JSDR_CATCH_ALL
 
 extern "C" int jsdr_fft_forward_f32(jsdr_fft *f, const float *iq, int batch, float *spec, int mem)
-{
+try {
     return fft_run(f, iq, fft::IN_F32, batch, 0, 0, spec, nullptr, fft::OUT_SPECTRUM, mem);
-}
+} JSDR_CATCH_ALL
