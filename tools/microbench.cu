@@ -109,6 +109,30 @@ __global__ void __launch_bounds__(1024) k_tput(double *out, long long *cyc, doub
             if (OP == 3) a[k] = (double)(__double2float_rn(a[k]) + 1.0f);   // F2F.F32.F64 + FADD + F2F.F64.F32
             if (OP == 4) f[k].x = __shfl_xor_sync(0xffffffffu, f[k].x, 1);
             if (OP == 5) asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(f[k].x) : "f"(f[k].y));
+            if (OP == 6) {                                       // half packed, half scalar: do the two FMA pipes overlap?
+                if (k & 1) {
+                    asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(f[k].x) : "f"(f[k].y));
+                } else {
+                    unsigned long long r, x = *reinterpret_cast<unsigned long long *>(&f[k]);
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %1;" : "=l"(r) : "l"(x));
+                    f[k] = *reinterpret_cast<float2 *>(&r);
+                }
+            }
+            if (OP == 7) {                                       // two packed to one scalar
+                if (k % 3 == 2) {
+                    asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(f[k].x) : "f"(f[k].y));
+                } else {
+                    unsigned long long r, x = *reinterpret_cast<unsigned long long *>(&f[k]);
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %1;" : "=l"(r) : "l"(x));
+                    f[k] = *reinterpret_cast<float2 *>(&r);
+                }
+            }
+            if (OP == 8) {                                       // packed add (FADD2)
+                unsigned long long r, x = *reinterpret_cast<unsigned long long *>(&f[k]);
+                asm volatile("add.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(x));
+                f[k] = *reinterpret_cast<float2 *>(&r);
+            }
+            if (OP == 9) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[k].x) : "f"(f[k].y));
         }
     }
     long long t1 = clock64();
@@ -193,8 +217,9 @@ int main()
     printf("__fdiv_rn (IEEE float division)                              %6.2f cycles per step\n", cyc0() / kIters);
 
     printf("## throughput, one SM with 1024 threads, 8 independent chains per thread (thread-operations per cycle per SM)\n");
-    const char *names[] = {"DADD", "DMUL", "FFMA2 (packed: 2 FMA per lane)", "F2F.F32.F64 + FADD + F2F.F64.F32", "SHFL.BFLY", "FFMA"};
-    for (int op = 0; op < 6; op++) {
+    const char *names[] = {"DADD", "DMUL", "FFMA2 (packed: 2 FMA per lane)", "F2F.F32.F64 + FADD + F2F.F64.F32", "SHFL.BFLY", "FFMA",
+                           "4 FFMA2 + 4 FFMA interleaved", "5-6 FFMA2 + 2-3 FFMA interleaved", "FADD2 (packed)", "FADD"};
+    for (int op = 0; op < 10; op++) {
         for (int rep = 0; rep < 2; rep++) {
             switch (op) {
             case 0: k_tput<0><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
@@ -202,7 +227,11 @@ int main()
             case 2: k_tput<2><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
             case 3: k_tput<3><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
             case 4: k_tput<4><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
-            default: k_tput<5><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
+            case 5: k_tput<5><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
+            case 6: k_tput<6><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
+            case 7: k_tput<7><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
+            case 8: k_tput<8><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
+            default: k_tput<9><<<1, 1024>>>(d_out, d_cyc, 1e-3); break;
             }
         }
         CK(cudaDeviceSynchronize());
