@@ -1,0 +1,245 @@
+"""Seeded differential runs of the tuner bank against the oracle (FUNcubeBPSKDemod.java:366-595).
+
+Each seed draws a whole scenario — rate, number of tuners (both sides of the 32-channel switch
+between the tile kernel and the streaming kernel), per-channel streams or one shared stream,
+s16 or float blocks, a sequence of ragged block lengths (including 0 and 1), tunings of either
+sign, retunes between blocks, the kernel mode — and every output of every block of a few
+channels must be bit-identical to the oracle's: decimator rows, matched-filter rows, bits, the
+sample index of every bit, the counters.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import jsdrcuda as J
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def scenario(seed):
+    rng = np.random.default_rng(1000 + seed)
+    rate = int(rng.choice([48000, 96000, 192000]))
+    nchan = int(rng.choice([1, 2, 5, 31, 32, 33, 47, 64, 96]))
+    shared = bool(rng.integers(0, 2)) and nchan > 1
+    s16 = bool(rng.integers(0, 2))
+    nblocks = int(rng.integers(3, 7))
+    max_block = int(rng.choice([700, 4096, 9600, 20000]))
+    lens = [int(rng.integers(0, max_block + 1)) for _ in range(nblocks)]
+    lens[int(rng.integers(0, nblocks))] = max_block
+    if seed % 4 == 0:
+        lens[0] = 1
+    if seed % 5 == 0:
+        lens[1] = 0
+    lim = rate / 2.2
+    tuning = rng.uniform(-lim, lim, nchan)
+    tuning[rng.integers(0, nchan)] = 12000.0
+    kernel = int(rng.choice([J.KERNEL_AUTO, J.KERNEL_AUTO, J.KERNEL_TILE, J.KERNEL_STREAM]))
+    retunes = {}                                              # block index -> [(chan, hz)]
+    for _ in range(int(rng.integers(0, 4))):
+        retunes.setdefault(int(rng.integers(1, nblocks)), []).append((int(rng.integers(0, nchan)), float(rng.uniform(-lim, lim))))
+    return rng, rate, nchan, shared, s16, lens, max_block, tuning, kernel, retunes
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))   # more seeds: a soak run
+def test_bank_scenarios_bit_exact(ctx, seed):
+    rng, rate, nchan, shared, s16, lens, max_block, tuning, kernel, retunes = scenario(seed)
+    adsc = J.AudioDescriptor(rate, blen=max_block * 4)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=max_block)
+    bank.set_kernel(kernel)
+    watch = sorted(set([0, nchan - 1, int(rng.integers(0, nchan))] + [c for v in retunes.values() for c, _ in v]))
+    orcs = {c: O.Bpsk(rate, float(tuning[c])) for c in watch}
+    what = f"seed {seed}: rate {rate}, {nchan} tuners, shared={shared}, s16={s16}, kernel {kernel}, blocks {lens}"
+    for k, n in enumerate(lens):
+        for c, hz in retunes.get(k, []):
+            bank.set_tuning(c, hz)
+            orcs[c].set_tuning(hz)
+        rows = 1 if shared else nchan
+        if s16:
+            raw = rng.integers(-32768, 32768, (rows, 2 * n)).astype(np.int16)
+            if n:
+                bank.receive_raw(raw if not shared else raw[0], shared=shared)
+            else:
+                bank.receive_raw(np.zeros(0, np.int16), shared=True)
+            fl = O.s16_to_float(raw.ravel()).reshape(rows, 2 * n)
+        else:
+            fl = rng.uniform(-1, 1, (rows, 2 * n)).astype(np.float32)
+            if n:
+                bank.receive(fl if not shared else fl[0], shared=shared)
+            else:
+                bank.receive(np.zeros(0, np.float32), shared=True)
+        nds = bank.last_nds()
+        ds, dm = bank.read_ds(), bank.read_dm()
+        bits, at = bank.read_bits()
+        for c in watch:
+            r = orcs[c].receive(fl[0 if shared else c])
+            assert nds == r["ds"].shape[0], f"{what}: block {k} channel {c} output count"
+            assert np.array_equal(ds[c], r["ds"]), f"{what}: block {k} channel {c} decimator"
+            assert np.array_equal(dm[c], r["dm"]), f"{what}: block {k} channel {c} matched filter"
+            assert np.array_equal(bits[c], r["bits"]), f"{what}: block {k} channel {c} bits"
+            assert np.array_equal(at[c], r["bit_at"]), f"{what}: block {k} channel {c} bit positions"
+    cnt = bank.counters()
+    for c in watch:
+        oc = orcs[c].counters()
+        assert (cnt[c, 0], cnt[c, 1], cnt[c, 2]) == (oc["raw"], oc["ds"], oc["bit"]), f"{what}: counters of channel {c}"
+    bank.close()
+
+
+FFT_N = [2, 3, 16, 100, 128, 256, 500, 512, 1000, 1024, 2048, 4096, 4410, 4800, 6000, 8192, 9600, 16384, 19200, 32768, 65536]
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))
+def test_fft_scenarios_against_the_binary64_oracle(ctx, seed):
+    """fft.java:190-224 on drawn shapes: any supported length (single-CTA, split, staged and
+    four-step paths), ragged batches, s16 blocks with a drawn I/Q correction or float blocks,
+    noise plus a tone of drawn level and bin (on or off the grid, either half, DC and Nyquist
+    included); every block's dB row within 1e-4 of full scale of the binary64 restatement, the
+    published maximum and its wrapping-int32 frequency exact."""
+    from test_gpu_parity import check_psd
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice(FFT_N))
+    if not J.fft_supported(n):
+        pytest.skip(f"no plan for N={n}")
+    rate = int(rng.choice([44100, 96000, 192000]))
+    batch = int(rng.integers(1, 10)) if n <= 19200 else int(rng.integers(1, 4))
+    s16 = bool(rng.integers(0, 2))
+    t = np.arange(n)
+    x = np.empty((batch, 2 * n), dtype=np.float64)
+    for b in range(batch):
+        k = rng.choice([0.0, n / 2, float(rng.integers(0, n)), float(rng.uniform(0, n))])
+        tone = rng.uniform(0.01, 0.7) * np.exp(2j * np.pi * (k * t / n + rng.uniform()))
+        noise = rng.uniform(-0.2, 0.2, (n, 2))
+        x[b, 0::2], x[b, 1::2] = tone.real + noise[:, 0], tone.imag + noise[:, 1]
+    f = J.fft(ctx, None, J.AudioDescriptor(rate), max_batch=batch, n=n)
+    if s16:
+        ic, qc = (int(rng.integers(-300, 300)), int(rng.integers(-300, 300))) if rng.integers(0, 2) else (0, 0)
+        raw = np.round(x * 32767).astype(np.int16)
+        psd, pk = f.receive_batch(raw, s16=True, ic=ic, qc=qc)
+        fl = np.stack([O.s16_to_float(raw[b], ic=ic, qc=qc) for b in range(batch)])
+    else:
+        fl = x.astype(np.float32)
+        psd, pk = f.receive_batch(fl)
+    f.close()
+    for b in range(batch):
+        check_psd(psd[b], fl[b], rate, n)
+        row = psd[b, :n]
+        assert pk[b] == int(np.argmax(row)) and psd[b, n + 1] == row.max()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))
+def test_demod_scenarios_bit_exact_without_nco(ctx, seed):
+    """demod.java:378-396,405-481 on drawn shapes: channels, band edges (the all-pass included),
+    detector mode, AGC, ragged blocks with carried FIR history / running mean / discriminator
+    state.  NCO off, so nothing transcendental enters and every float and every s16 is exact."""
+    rng = np.random.default_rng(9000 + seed)
+    rate = int(rng.choice([44100, 48000, 96000, 192000]))
+    nchan = int(rng.choice([1, 2, 3, 7, 33]))
+    mode = int(rng.integers(0, 5))
+    doagc = bool(rng.integers(0, 2))
+    max_block = int(rng.choice([333, 2048, 9600]))
+    lens = [int(rng.integers(1, max_block + 1)) for _ in range(int(rng.integers(2, 6)))] + [max_block]
+    d = J.demod(ctx, J.AudioDescriptor(rate), nchan=nchan, max_block=max_block, dofir=True, dodwn=False)
+    d.set_mode(mode, doagc)
+    os_, lilq = [], [np.zeros(2, np.float32) for _ in range(nchan)]
+    for c in range(nchan):
+        if rng.integers(0, 6) == 0:
+            lo, hi = J.INT_MIN, 0                                 # all-pass (demod.java:343-346)
+        else:
+            lo = int(rng.integers(-rate // 2, rate // 2 - 200))
+            hi = int(rng.integers(lo + 100, rate // 2))
+        d.weights(lo, hi, chan=c)
+        o = O.Demod(rate, True, False)
+        o.weights(O.INT_MIN if lo == J.INT_MIN else lo, hi)
+        os_.append(o)
+    scale = float(rng.choice([0.01, 0.3, 1.0]))
+    for n in lens:
+        x = (rng.standard_normal((nchan, 2 * n)) * scale).astype(np.float32)
+        audio, ma = d.receive_audio(x)
+        for c in range(nchan):
+            ref_a, ref_ma = O.demod_detect(os_[c].receive(x[c]), mode, rate, doagc, lilq[c])
+            assert np.array_equal(audio[c], ref_a), (seed, rate, nchan, mode, doagc, n, c)
+            assert np.array_equal(ma[c], ref_ma, equal_nan=True), (seed, rate, nchan, mode, doagc, n, c)
+    d.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))
+def test_fir_and_waterfall_scenarios_bit_exact(ctx, seed):
+    """fir.java:169-228 (int samples x double taps, (int) truncation and saturation, carried
+    delay line, wrapping complex multiply) and waterfall.java:90-107 on drawn shapes."""
+    rng = np.random.default_rng(13000 + seed)
+    rate = float(rng.choice([8000.0, 44100.0, 96000.0]))
+    f, o = J.fir(ctx, rate), O.Fir(rate)
+    f1 = int(rng.integers(0, int(rate) // 2 - 200))
+    f2 = int(rng.integers(f1 + 100, int(rate) // 2))
+    assert np.array_equal(f.weights(f1, f2), o.weights(f1, f2))
+    for _ in range(int(rng.integers(2, 6))):
+        n = int(rng.integers(1, 20000))
+        span = int(rng.choice([100, 32768, 1 << 31]))
+        x = rng.integers(-span, span, n).astype(np.int32)
+        assert np.array_equal(f.filter(x)[0], o.filter(x)), (seed, n, span)
+    m = int(rng.integers(1, 5000))
+    a = rng.integers(-(1 << 31), 1 << 31, (m, 2)).astype(np.int32)
+    b = rng.integers(-(1 << 31), 1 << 31, (m, 2)).astype(np.int32)
+    assert np.array_equal(f.complex_mod(a, b), O.complex_mod(a, b))
+    f.close()
+    n = int(rng.choice([128, 1000, 4096, 9600, 19200]))
+    width = int(rng.integers(1, n + 1))
+    rows = int(rng.integers(1, 9))
+    psd = rng.uniform(-140, 10, (rows, n + 2)).astype(np.float32)
+    psd[rng.integers(0, rows), rng.integers(0, n)] = -np.inf
+    pix = J.waterfall_rows(ctx, psd, width)
+    for r in range(rows):
+        assert np.array_equal(pix[r], O.waterfall_row(psd[r], width)), (seed, n, width, r)
+
+
+@pytest.mark.parametrize("seed", range(max(1, int(os.environ.get("JSDR_FUZZ_SEEDS", "24")) // 4)))
+def test_frame_stage_scenarios(ctx, seed):
+    """Sync correlator + FECDecode (FUNcubeBPSKDemod.java:553-574, FECDecoder.java:703-852) on
+    drawn damage: two frames whose RS blocks carry 0..22 symbol errors behind the convolutional
+    code AND whose channel symbols are flipped in 0..300 places in front of it, so Viterbi, both
+    RS outcomes (corrected / -1 / miscorrected) and the channel-error count are all exercised.
+    Frame list, return values, payloads and cntFEC / cntDec equal the oracle's."""
+    import rs_warp_model as M
+    from oracle import siggen
+    from test_gpu_fec import mettab, oracle_frames
+    alpha, index, poly = (J.probe_table(t).tolist() for t in ("ALPHA_TO", "INDEX_OF", "RS_poly"))
+    gf = M.GF(alpha, index)
+    par = M.rs_parity_map(alpha, index, poly)
+    scr, sync = J.probe_table("Scrambler").tolist(), J.probe_table("SYNC_VECTOR").tolist()
+    rng = np.random.default_rng(17000 + seed)
+    frames = []
+    for _ in range(2):
+        blocks = []
+        for r in range(2):
+            d = rng.integers(0, 256, 128).tolist()
+            cw = d + M.rs_parity(d, par, gf)
+            for q in rng.choice(160, int(rng.integers(0, 23)), replace=False):
+                cw[q] ^= int(rng.integers(1, 256))
+            blocks.append(cw)
+        sym = M.symbols_from_blocks(blocks, scr, sync)
+        flips = rng.choice(sym.size, int(rng.choice([0, 10, 100, 300])), replace=False)
+        sym[flips] ^= 1
+        frames.append(sym)
+    sig = siggen.make_iq_s16(None, rate=96000, ebn0_db=None, pad_to=9600, symbols=frames)
+    fbuf = O.s16_to_float(sig)
+    adsc = J.AudioDescriptor(96000)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0])
+    bank.enable_fec(mettab(), max_frames=8)
+    orc = O.Bpsk(96000, 12000.0, do_fec=True)
+    got, allbits = [], []
+    for k in range(fbuf.size // (2 * adsc.samples)):
+        blk = fbuf[2 * k * adsc.samples: 2 * (k + 1) * adsc.samples]
+        bank.receive(blk)
+        got += bank.read_frames()
+        allbits.append(orc.receive(blk)["bits"])
+    ref = oracle_frames(np.concatenate(allbits))
+    assert len(got) == len(ref), (seed, len(got), len(ref))
+    for (ch, at, err, data), (rat, rerr, rdata) in zip(got, ref):
+        assert at == rat and err == rerr, (seed, at, rat, err, rerr)
+        if rerr >= 0:
+            assert np.array_equal(data, rdata)
+    fec, dec = bank.fec_counters()
+    oc = orc.counters()
+    assert (int(fec[0]), int(dec[0])) == (oc["fec"], oc["dec"]), seed
+    bank.close()
