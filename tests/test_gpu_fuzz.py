@@ -243,3 +243,39 @@ def test_frame_stage_scenarios(ctx, seed):
     oc = orc.counters()
     assert (int(fec[0]), int(dec[0])) == (oc["fec"], oc["dec"]), seed
     bank.close()
+
+
+@pytest.mark.parametrize("seed", range(max(1, int(os.environ.get("JSDR_FUZZ_SEEDS", "24")) // 6)))
+def test_autotune_scenarios(ctx, seed):
+    """doBufferFFT (FUNcubeBPSKDemod.java:406-464) on drawn carriers in either scanned band, with
+    and without noise: the centre bin and every bit identical to the oracle, samples within
+    1e-9 of full scale (the two sides transform with different binary64 FFTs)."""
+    from oracle import siggen
+    rng = np.random.default_rng(21000 + seed)
+    rate = int(rng.choice([96000, 192000]))
+    adsc = J.AudioDescriptor(rate)
+    n = adsc.samples
+    upper = bool(rng.integers(0, 2))
+    lo_bin, hi_bin = (n // 4 + 300, n // 2 - 300) if upper else (300, n // 4 - 300)
+    carrier = float(rng.uniform(lo_bin, hi_bin)) * rate / n
+    ebn0 = [None, 16.0, 20.0][int(rng.integers(0, 3))]
+    sig = siggen.make_iq_s16(siggen.random_payloads(1), rate=rate, carrier_hz=carrier, ebn0_db=ebn0,
+                             noise_seed=int(rng.integers(1, 1 << 30)), pad_to=n)
+    fbuf = O.s16_to_float(sig)
+    bank = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=[12000.0])
+    bank.set_autotune(True, upper)
+    orc = O.Bpsk(rate, 12000.0)
+    orc.s.doUp = int(upper)
+    worst, nbits = 0.0, 0
+    for k in range(min(fbuf.size // (2 * n), 12)):
+        blk = fbuf[2 * k * n: 2 * (k + 1) * n]
+        bank.receive(blk)
+        r = orc.receive(blk, autotune=True)
+        assert int(bank.centre_bins()[0]) == r["centre_bin"], (seed, k)
+        ds = bank.read_ds()[0]
+        assert ds.shape == r["ds"].shape
+        worst = max(worst, float(np.max(np.abs(ds - r["ds"]))) / (0.9 * 32768.0))
+        assert np.array_equal(bank.read_bits()[0][0], r["bits"]), (seed, k)
+        nbits += r["bits"].size
+    assert worst <= 1e-9 and nbits > 300, (seed, worst, nbits)
+    bank.close()
