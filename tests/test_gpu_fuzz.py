@@ -279,3 +279,76 @@ def test_autotune_scenarios(ctx, seed):
         nbits += r["bits"].size
     assert worst <= 1e-9 and nbits > 300, (seed, worst, nbits)
     bank.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))
+def test_pump_scenarios_equal_the_separate_handlers(ctx, seed):
+    """jsdr_pump_receive_s16 / jsdr_pump_waterfall_s16 (JavaAudio.java:262-304) on drawn shapes —
+    channel counts on both sides of every chunk boundary of the pipelined host path, blocks per
+    call, FFT length, I/Q correction, host or device buffers, PSD or pixel rows — against the
+    spectrum handler and the tuner bank called one after the other on the same bytes (each of
+    which the tests above tie to the oracle): identical PSD rows / pixel rows, peak bins,
+    decimator rows and bits."""
+    rng = np.random.default_rng(25000 + seed)
+    rate = int(rng.choice([96000, 192000]))
+    n = int(rng.choice([128, 1000, 1024, 4096, 4800]))
+    nchan = int(rng.choice([1, 7, 8, 15, 16, 17, 33, 37, 130, 200]))
+    nblk = int(rng.integers(1, 4))
+    ic, qc = (int(rng.integers(-500, 500)), int(rng.integers(-500, 500))) if rng.integers(0, 2) else (0, 0)
+    device = bool(rng.integers(0, 2))
+    pixels = bool(rng.integers(0, 2))
+    width = int(rng.integers(1, n + 1))
+    S, rows = nblk * n, nchan * nblk
+    raw = rng.integers(-32768, 32768, (nchan, 2 * S)).astype(np.int16)
+    tuning = rng.uniform(-rate / 2.2, rate / 2.2, nchan)
+    adsc = J.AudioDescriptor(rate, blen=S * 4)
+    what = (seed, rate, n, nchan, nblk, ic, qc, device, pixels, width)
+    # the two handlers, separately
+    f1 = J.fft(ctx, None, adsc, max_batch=rows, n=n)
+    b1 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S)
+    psd1, pk1 = f1.receive_batch(raw.reshape(rows, 2 * n), s16=True, ic=ic, qc=qc)
+    b1.receive_raw(raw, ic=ic, qc=qc, shared=False)
+    ds1, bits1 = b1.read_ds(), b1.read_bits()[0]
+    # the pump
+    f2 = J.fft(ctx, None, adsc, max_batch=rows, n=n)
+    b2 = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, max_block=S)
+    if device:
+        d_raw = ctx.dev_alloc(raw.nbytes)
+        d_raw.upload(raw)
+        d_pk = ctx.dev_alloc(rows * 4)
+        if pixels:
+            d_pix, d_peak = ctx.dev_alloc(rows * width * 4), ctx.dev_alloc(rows * 8)
+            J.pump_waterfall_s16(f2, b2, d_raw.ptr, nblk, width, d_pix.ptr, d_peak.ptr, d_pk.ptr, mem=J.MEM_DEVICE, ic=ic, qc=qc)
+            ctx.sync()
+            pix2 = d_pix.download(np.int32, rows * width).reshape(rows, width)
+            peak2 = d_peak.download(np.float32, rows * 2).reshape(rows, 2)
+            d_pix.free()
+            d_peak.free()
+        else:
+            d_psd = ctx.dev_alloc(rows * (n + 2) * 4)
+            J.pump_receive_s16(f2, b2, d_raw.ptr, nblk, d_psd.ptr, d_pk.ptr, mem=J.MEM_DEVICE, ic=ic, qc=qc)
+            ctx.sync()
+            psd2 = d_psd.download(np.float32, rows * (n + 2)).reshape(rows, n + 2)
+            d_psd.free()
+        pk2 = d_pk.download(np.int32, rows)
+        d_pk.free()
+        d_raw.free()
+    else:
+        pk2 = np.zeros(rows, np.int32)
+        if pixels:
+            pix2, peak2 = np.zeros((rows, width), np.int32), np.zeros((rows, 2), np.float32)
+            J.pump_waterfall_s16(f2, b2, raw, nblk, width, pix2, peak2, pk2, ic=ic, qc=qc)
+        else:
+            psd2 = np.zeros((rows, n + 2), np.float32)
+            J.pump_receive_s16(f2, b2, raw, nblk, psd2, pk2, ic=ic, qc=qc)
+    assert np.array_equal(pk2, pk1), what
+    if pixels:
+        assert np.array_equal(pix2, J.waterfall_rows(ctx, psd1, width)), what
+        assert np.array_equal(peak2, psd1[:, n:]), what
+    else:
+        assert np.array_equal(psd2, psd1), what
+    assert np.array_equal(b2.read_ds(), ds1), what
+    bits2 = b2.read_bits()[0]
+    assert all(np.array_equal(x, y) for x, y in zip(bits2, bits1)), what
+    for h in (f1, f2, b1, b2):
+        h.close()
