@@ -137,7 +137,8 @@ int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz);       /* :174-189 *
 /* The FFT auto-tune variant, doBufferFFT (FUNcubeBPSKDemod.java:406-464; config keys
  * "FUNcube<i>-bpsk-dofft" / "-upper", :198-200): when dofft is set every receive call
  * must carry exactly max_block_samples samples (the transform length is the block
- * length, :421).  Forward transform in binary64, 100-bin boxcar arg-max over the lower
+ * length, :421; 1024..115712 samples with no prime factor beyond 7 — rate/10 of every
+ * supported rate qualifies — otherwise set_autotune answers JSDR_EUNSUPPORTED).  Forward transform in binary64, 100-bin boxcar arg-max over the lower
  * (or, do_upper, upper) quarter band, smoothed / gated / clamped centre bin, 204 bins
  * moved to DC, inverse transform scaled by 1/n, decimator fed (re, re) (:461-463).
  * read_centre returns what the reference publishes as "<name>-bpsk-centre" (:456). */

@@ -1171,6 +1171,9 @@ int launch_stream(jsdr_bpsk *b, const MixParams &mp, int S)
 // doBufferFFT (:406-464) for every channel of the bank: binary64 forward transform, search,
 // 204 bins to DC, inverse transform, decimator on the real part.  The tuner phase is not
 // advanced (the reference's FFT variant never calls RxMixTuner).
+// k_at_search keeps the N/4 magnitudes of the scanned band (+ 64 words) in shared memory as doubles
+constexpr int kAutoTuneMaxN = 115712;                  // 8 * (N/4 + 64) <= 232448 bytes
+
 template <int FMT>
 int autotune_block(jsdr_bpsk *b, const void *d_in, int S, long long chan_stride, int ic, int qc, int n0, int NO)
 {
@@ -1191,7 +1194,7 @@ int autotune_block(jsdr_bpsk *b, const void *d_in, int S, long long chan_stride,
         JSDR_CUDA(cudaMemsetAsync(b->d_at_state, 0, sizeof(AutoTuneState) * (size_t)nchan, ctx->stream));
     }
     JSDR_REQUIRE(fftg::make_plan(N).nstages > 0, JSDR_EUNSUPPORTED, "block length has a prime factor other than 2, 3, 5, 7");
-    JSDR_REQUIRE(N >= 1024, JSDR_EUNSUPPORTED, "auto-tune needs blocks of at least 1024 samples");
+    JSDR_REQUIRE(N >= 1024 && N <= kAutoTuneMaxN, JSDR_EUNSUPPORTED, "auto-tune needs blocks of 1024 to 115712 samples");
     const long long total = (long long)nchan * N;
     k_at_load<FMT><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in, chan_stride, S, nchan, ic, qc, b->d_at_work[0]);
     JSDR_TRY(launched(ctx, "k_at_load"));
@@ -1581,6 +1584,13 @@ try {
 extern "C" int jsdr_bpsk_set_autotune(jsdr_bpsk *b, int dofft, int do_upper)
 try {
     JSDR_REQUIRE(b, JSDR_EINVAL, "null argument");
+    if (dofft) {                                       // the transform length is the block length (:421)
+        const int N = b->max_block;
+        JSDR_REQUIRE(N >= 1024, JSDR_EUNSUPPORTED, "auto-tune needs blocks of at least 1024 samples");
+        JSDR_REQUIRE(N <= kAutoTuneMaxN, JSDR_EUNSUPPORTED,
+                     "auto-tune supports blocks of up to 115712 samples (the band search keeps N/4 bins in shared memory)");
+        JSDR_REQUIRE(fftg::make_plan(N).nstages > 0, JSDR_EUNSUPPORTED, "block length has a prime factor other than 2, 3, 5, 7");
+    }
     b->dofft = dofft != 0;
     b->doUp = do_upper != 0;
     return JSDR_OK;

@@ -62,6 +62,25 @@ def test_autotune_needs_whole_blocks(ctx):
     bank.close()
 
 
+def test_autotune_block_length_limits(ctx):
+    """The transform length is the bank's block length: below 1024, above 115712 (the band search
+    keeps N/4 bins in shared memory) or with a prime factor beyond 7 the switch is refused with a
+    status, not found out by a failing launch."""
+    for mb in (1000, 131072, 2 * 11 * 1024):
+        bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(96000, blen=4 * mb), tuning=[12000.0], max_block=mb)
+        with pytest.raises(J.JsdrError) as e:
+            bank.set_autotune(True)
+        assert e.value.code == -4, (mb, e.value)               # JSDR_EUNSUPPORTED
+        bank.set_autotune(False)                               # switching it off is always fine
+        bank.receive(np.zeros(2 * 100, np.float32))
+        bank.close()
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(96000, blen=4 * 115200), tuning=[12000.0], max_block=115200)
+    bank.set_autotune(True)
+    bank.receive(np.random.default_rng(0).uniform(-0.5, 0.5, 2 * 115200).astype(np.float32))
+    assert bank.last_nds() == 11520
+    bank.close()
+
+
 @pytest.mark.parametrize("n", [32768, 65536, 6000, 2 * 3 * 5 * 7 * 16])
 def test_fft_staged_path_lengths_without_a_single_cta_plan(ctx, n):
     """BASELINE config 3's sweep tops out at 65536: those lengths (and any other
