@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cmath>
 #include <stdlib.h>
 #include <string.h>
 
@@ -81,6 +82,10 @@ __device__ __forceinline__ double phase_step(double p, double inc)
 __device__ __forceinline__ int table_index(double p)
 {
     const double t = __dmul_rn(p, 256.0);
+    // A phase beyond 4pi only happens for a tuning above the sample rate (inc > 2pi: the single
+    // subtraction of :385 no longer keeps up and tuPhase grows without bound).  The reference then
+    // takes Java's saturating (int) of the quotient, % 256 of a non-negative int: do exactly that.
+    if (!(p < 16.0)) return __double2int_rz(__ddiv_rn(t, kTwoPi)) & 255;
     // a*2^20 + 1.5*2^52: the low word of the sum is round(a*2^20) (a < 2^9)
     const double y = __fma_rn(t, kInvTwoPi * 1048576.0, 6755399441055744.0);
     const int yi = __double2loint(y);
@@ -1452,6 +1457,8 @@ try {
     JSDR_REQUIRE(ctx && out && tuning_hz, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(rate >= 9600 && rate <= 64 * 9600 && nchan > 0 && nchan <= 65535 && max_block_samples > 0,
                  JSDR_EINVAL, "need 9600 <= rate <= 614400, 0 < nchan < 65536, max_block_samples > 0");
+    for (int c = 0; c < nchan; c++)
+        JSDR_REQUIRE(std::isfinite(tuning_hz[c]), JSDR_EINVAL, "every tuning must be a finite frequency (the reference's comes from an int config key or the dialog, :175-195)");
     JSDR_TRY(ctx->bind());
     jsdr_bpsk *b = new jsdr_bpsk();
     b->ctx = ctx;
@@ -1627,6 +1634,7 @@ try {
 extern "C" int jsdr_bpsk_set_tuning(jsdr_bpsk *b, int chan, double hz)
 try {
     JSDR_REQUIRE(b && chan >= 0 && chan < b->nchan, JSDR_EINVAL, "bad channel");
+    JSDR_REQUIRE(std::isfinite(hz), JSDR_EINVAL, "tuning must be a finite frequency (the reference's comes from an int config key or the dialog, :175-195)");
     JSDR_TRY(b->ctx->bind());
     // the scout may be running ahead with the old increment: let it finish and drop its plan
     JSDR_CUDA(cudaStreamSynchronize(b->ctx->side));

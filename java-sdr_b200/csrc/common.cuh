@@ -22,7 +22,8 @@ void set_error(const char *fmt, ...);
         if (_e != cudaSuccess) {                                                     \
             jsdr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,             \
                             cudaGetErrorString(_e));                                 \
-            return JSDR_ECUDA;                                                       \
+            cudaGetLastError(); /* reported: the next launch check must not see it */ \
+            return _e == cudaErrorMemoryAllocation ? JSDR_ENOMEM : JSDR_ECUDA;       \
         }                                                                            \
     } while (0)
 

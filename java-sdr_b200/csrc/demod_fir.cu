@@ -225,6 +225,7 @@ extern "C" int jsdr_demod_create(jsdr_ctx *ctx, int rate, int nchan, int max_blo
 try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(rate > 0 && nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
+    JSDR_REQUIRE(nchan <= 65535, JSDR_EINVAL, "at most 65535 channels per handle (the channel is the grid's y index)");
     JSDR_TRY(ctx->bind());
     jsdr_demod *d = new jsdr_demod();
     d->ctx = ctx;
@@ -604,6 +605,7 @@ extern "C" int jsdr_fir_create(jsdr_ctx *ctx, int nchan, int max_block_samples, 
 try {
     JSDR_REQUIRE(ctx && out, JSDR_EINVAL, "null argument");
     JSDR_REQUIRE(nchan > 0 && max_block_samples > 0, JSDR_EINVAL, "sizes must be positive");
+    JSDR_REQUIRE(nchan <= 65535, JSDR_EINVAL, "at most 65535 channels per handle (the channel is the grid's y index)");
     JSDR_TRY(ctx->bind());
     jsdr_fir *f = new jsdr_fir();
     f->ctx = ctx;

@@ -59,3 +59,39 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py", ".java")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "orc_" not in txt and "jsdr_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_null_handles_and_pointers_come_back_as_status_codes():
+    """Every entry point called with null handles / null pointers and a range of scalar values
+    answers a negative status (destroy of a null handle is a no-op): nothing dereferences before
+    it checks.  In a child process, so that a crash is a failed assertion and not a dead run."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys
+import jsdrcuda as J
+lib = J.lib()
+bad = []
+for iv in (0, 1, 2, 3, 21, 4096, -1, 2**31 - 1):
+    for name, args in sorted(J._SIGS.items()):
+        if name in ("jsdr_abi_version", "jsdr_fft_supported"):
+            continue
+        vals = []
+        for a in args:
+            if a in (C.c_float, C.c_double):
+                vals.append(a(1000.0))
+            elif a in (C.c_int, C.c_int64, C.c_uint32, C.c_size_t):
+                vals.append(a(iv & 0xffffffff) if a is C.c_uint32 else a(max(iv, 0)) if a is C.c_size_t else a(iv))
+            else:
+                vals.append(None)
+        rc = getattr(lib, name)(*vals)
+        if not (rc < 0 or (rc == 0 and name.endswith("_destroy"))):
+            bad.append((name, iv, rc))
+        elif rc < 0 and not lib.jsdr_last_error():
+            bad.append((name, iv, "no message"))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+"""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(jsdrcuda.__file__)), os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])

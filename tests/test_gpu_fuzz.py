@@ -352,3 +352,30 @@ def test_pump_scenarios_equal_the_separate_handlers(ctx, seed):
     assert all(np.array_equal(x, y) for x, y in zip(bits2, bits1)), what
     for h in (f1, f2, b1, b2):
         h.close()
+
+
+@pytest.mark.parametrize("kernel,s16", [(J.KERNEL_TILE, False), (J.KERNEL_STREAM, True), (J.KERNEL_STREAM, False)])
+def test_bank_absurd_but_finite_tunings_follow_the_reference(ctx, kernel, s16):
+    """Tunings far outside the band are finite numbers the reference would take from its dialog
+    (FUNcubeBPSKDemod.java:175-188): the phase then grows without bound and the table index comes
+    from Java's saturating (int) cast.  The bank must neither hang nor differ."""
+    rate, n = 96000, 4800
+    tuning = [1e300, 250000.0, -1e9, 0.75 * rate, 0.0, -0.0, 1e-300, 47999.9, 96000.0, 96001.0, 1e7] + list(np.linspace(500.0, 40000.0, 29))
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate, blen=4 * n), tuning=tuning, max_block=n)
+    bank.set_kernel(kernel)
+    orcs = [O.Bpsk(rate, t) for t in tuning[:13]]
+    rng = np.random.default_rng(77)
+    for k in range(3):
+        if s16:
+            raw = rng.integers(-32768, 32768, 2 * n).astype(np.int16)
+            bank.receive_raw(raw, shared=True)
+            x = O.s16_to_float(raw)
+        else:
+            x = rng.uniform(-1, 1, 2 * n).astype(np.float32)
+            bank.receive(x, shared=True)
+        ds, bits = bank.read_ds(), bank.read_bits()[0]
+        for c, o in enumerate(orcs):
+            r = o.receive(x)
+            assert np.array_equal(ds[c], r["ds"], equal_nan=True), (k, tuning[c])
+            assert np.array_equal(bits[c], r["bits"]), (k, tuning[c])
+    bank.close()
