@@ -1240,6 +1240,8 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         b->ds_read_pending = 0;
     }
     b->last_nds = 0;
+    if (b->stages >= 2) JSDR_TRY(ensure_stage_buffers(b));   // (before the empty-block return: the reads that follow an
+                                                             //  empty FIRST block answer "nothing", not "stage has not run")
     if (S == 0) {
         JSDR_CUDA(cudaMemsetAsync(b->d_nbits, 0, sizeof(int32_t) * b->nchan, ctx->aux));
         if (b->fec && b->stages >= 3 && b->d_bits) JSDR_TRY(jsdr_fec_after_bits(b));   // no bits: no frames either
@@ -1249,7 +1251,6 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
     const int NO = (b->ds_cnt + S) / D;
     const int n0 = D - 1 - b->ds_cnt;
     const int nchan = b->nchan;
-    if (b->stages >= 2) JSDR_TRY(ensure_stage_buffers(b));
 
     // ---- fork: data-independent work on the side stream.  The tuner plan for this
     // block was normally computed while the previous block was being processed.

@@ -379,3 +379,37 @@ def test_bank_absurd_but_finite_tunings_follow_the_reference(ctx, kernel, s16):
             assert np.array_equal(ds[c], r["ds"], equal_nan=True), (k, tuning[c])
             assert np.array_equal(bits[c], r["bits"]), (k, tuning[c])
     bank.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("JSDR_FUZZ_SEEDS", "24"))))
+def test_bank_filter_and_rate_shapes(ctx, seed):
+    """Every decimation the rate rule allows (rate / 9600 from 1 to 64, FUNcubeBPSKDemod.java:476)
+    with drawn decimator filters of 1..128 taps (jsdr_bpsk_set_ds_filter): the compiled shapes and
+    the generic loop, the tile and the streaming kernel, against the oracle with the same taps."""
+    rng = np.random.default_rng(31000 + seed)
+    D = int(rng.choice([1, 2, 3, 5, 7, 10, 20, 33, 64]))
+    rate = min(9600 * D + int(rng.integers(0, 9600)) * int(rng.integers(0, 2)), 614400)   # integer division :476
+    ntaps = int(rng.choice([1, 2, 3, 26, 27, 28, 63, 64, 65, 127, 128]))
+    taps = rng.uniform(-1, 1, ntaps) if rng.integers(0, 2) else np.hamming(ntaps + 2)[1:-1] / max(ntaps, 1)
+    nchan = int(rng.choice([1, 3, 32, 45]))
+    max_block = int(rng.choice([1, 50, 999, 6400]))
+    lens = [int(rng.integers(0, max_block + 1)) for _ in range(int(rng.integers(2, 6)))] + [max_block]
+    tuning = rng.uniform(-rate / 2.2, rate / 2.2, nchan)
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate, blen=4 * max_block), tuning=tuning, max_block=max_block)
+    bank.set_ds_filter(taps)
+    bank.set_kernel(int(rng.choice([J.KERNEL_AUTO, J.KERNEL_TILE, J.KERNEL_STREAM])))
+    watch = sorted({0, nchan - 1, int(rng.integers(0, nchan))})
+    orcs = {c: O.Bpsk(rate, float(tuning[c]), ds_taps=taps) for c in watch}
+    what = (seed, rate, D, ntaps, nchan, lens)
+    for k, n in enumerate(lens):
+        x = rng.uniform(-1, 1, (nchan, 2 * n)).astype(np.float32)
+        bank.receive(x if n else np.zeros(0, np.float32), shared=(n == 0))
+        ds, dm = bank.read_ds(), bank.read_dm()
+        bits = bank.read_bits()[0]
+        for c in watch:
+            r = orcs[c].receive(x[c])
+            assert ds[c].shape == r["ds"].shape, (what, k, c)
+            assert np.array_equal(ds[c], r["ds"]), (what, k, c)
+            assert np.array_equal(dm[c], r["dm"]), (what, k, c)
+            assert np.array_equal(bits[c], r["bits"]), (what, k, c)
+    bank.close()
