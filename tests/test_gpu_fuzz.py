@@ -413,3 +413,112 @@ def test_bank_filter_and_rate_shapes(ctx, seed):
             assert np.array_equal(dm[c], r["dm"]), (what, k, c)
             assert np.array_equal(bits[c], r["bits"]), (what, k, c)
     bank.close()
+
+
+def test_long_runs_do_not_drift(ctx):
+    """Recurrences that run for the life of a handle — the tuner phase and its fixed-point
+    shadow (re-anchored at exact checkpoints), the VCO phase, the 65-slot matched-filter rotation
+    (cntDS % 65), the bit-timing IIRs, demod.java's float NCO phase (:424-433) — over 1500 blocks
+    (14.4 M samples per channel): still bit-identical (bank) / within 1e-6 (demod NCO, whose
+    cos/sin come from a different libm) at the end, every block checked on the way."""
+    rate, n, nblk = 96000, 9600, 1500
+    tuning = [12000.0, -31234.5, 47000.0, 3.0]
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate), tuning=tuning)
+    orcs = [O.Bpsk(rate, t) for t in tuning]
+    d = J.demod(ctx, J.AudioDescriptor(rate), nchan=1, max_block=n)
+    d.weights(9000, 15000)
+    od = O.Demod(rate, True, True)
+    od.weights(9000, 15000)
+    rng = np.random.default_rng(99)
+    nbits = 0
+    for k in range(nblk):
+        x = rng.uniform(-0.5, 0.5, 2 * n).astype(np.float32)
+        bank.receive(x, shared=True)
+        ds, bits = bank.read_ds(), bank.read_bits()[0]
+        for c, o in enumerate(orcs):
+            r = o.receive(x)
+            assert np.array_equal(ds[c], r["ds"]), (k, c)
+            assert np.array_equal(bits[c], r["bits"]), (k, c)
+            nbits += r["bits"].size
+        y = d.receive(x)[0]
+        assert np.max(np.abs(y - od.receive(x))) <= 1e-6, k
+    cnt = bank.counters()
+    for c, o in enumerate(orcs):
+        oc = o.counters()
+        assert (cnt[c, 0], cnt[c, 1], cnt[c, 2]) == (oc["raw"], oc["ds"], oc["bit"]) and oc["raw"] == nblk * n
+    assert nbits > 10000
+    bank.close()
+    d.close()
+
+
+@pytest.mark.parametrize("seed", range(max(1, int(os.environ.get("JSDR_FUZZ_SEEDS", "24")) // 3)))
+def test_binary32_decimator_stays_within_tolerance(ctx, seed):
+    """JSDR_PREC_F32 (channeliser use, stages == 1): same exact table index sequence, mix and FIR
+    in binary32 — within 1e-4 of full scale of the binary64 oracle (the north_star's bar; measured
+    ~2e-6) on drawn shapes, s16 and float input, compiled (27/10, 27/20, 64/20) and generic taps."""
+    rng = np.random.default_rng(37000 + seed)
+    D, ntaps = [(10, 27), (20, 27), (20, 64), (10, 40), (5, 27)][int(rng.integers(0, 5))]
+    rate = 9600 * D
+    nchan = int(rng.choice([8, 40, 70]))
+    n = int(rng.choice([999, 4800, 19200]))
+    taps = np.sinc((np.arange(ntaps) - (ntaps - 1) / 2) * 0.9 / D) * np.hamming(ntaps)
+    taps /= taps.sum()
+    tuning = rng.uniform(500.0, rate / 2.2, nchan)
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(rate, blen=4 * n), tuning=tuning, max_block=n, stages=1)
+    if ntaps != 27 or rng.integers(0, 2):
+        bank.set_ds_filter(taps)
+        otaps = taps
+    else:
+        otaps = None
+    bank.set_precision(J.PREC_F32)
+    watch = sorted({0, nchan - 1, int(rng.integers(0, nchan))})
+    orcs = {c: O.Bpsk(rate, float(tuning[c]), ds_taps=otaps, stages=1) for c in watch}
+    s16 = bool(rng.integers(0, 2))
+    worst = 0.0
+    for k in range(3):
+        if s16:
+            raw = rng.integers(-32768, 32768, (nchan, 2 * n)).astype(np.int16)
+            bank.receive_raw(raw, shared=False)
+            x = O.s16_to_float(raw.ravel()).reshape(nchan, 2 * n)
+        else:
+            x = rng.uniform(-1, 1, (nchan, 2 * n)).astype(np.float32)
+            bank.receive(x, shared=False)
+        ds = bank.read_ds()
+        for c in watch:
+            r = orcs[c].receive(x[c])["ds"]
+            assert ds[c].shape == r.shape
+            worst = max(worst, float(np.max(np.abs(ds[c] - r))) / (0.9 * 32768.0))
+    assert worst <= 1e-4, (seed, D, ntaps, nchan, n, s16, worst)
+    bank.close()
+
+
+def test_frame_capacity_overflow_is_counted_not_written(ctx):
+    """More frames in one call than max_frames: *nframes says how many were detected, only
+    max_frames are returned, nothing is written past the caller's arrays, cntFEC / cntDec still
+    count every one (FUNcubeBPSKDemod.java:563-571)."""
+    from oracle import siggen
+    from test_gpu_fec import mettab
+    pl = siggen.random_payloads(3)
+    sig = siggen.make_iq_s16(pl, rate=96000, ebn0_db=None, pad_to=9600)
+    fbuf = O.s16_to_float(sig)
+    n = fbuf.size // 2                                       # the whole signal as ONE block: 3 frames per channel
+    nchan = 5
+    bank = J.FUNcubeBPSKDemod(ctx, None, J.AudioDescriptor(96000, blen=4 * n), tuning=[12000.0] * nchan, max_block=n)
+    bank.enable_fec(mettab(), max_frames=1)
+    bank.receive(fbuf, shared=True)
+    cap = 4                                                  # fewer than the 15 detected
+    nf = C_int32 = np.zeros(1, np.int32)
+    chan = np.full(cap + 2, -7, np.int32)
+    at = np.full(cap + 2, -7, np.int64)
+    err = np.full(cap + 2, -7, np.int32)
+    data = np.full((cap + 2, 256), 0xEE, np.uint8)
+    J._ck(J.lib().jsdr_bpsk_read_frames(bank.h, J._ptr(nf), J._ptr(chan), J._ptr(at), J._ptr(err), J._ptr(data), cap))
+    assert nf[0] == 3 * nchan, nf
+    assert np.all(chan[cap:] == -7) and np.all(at[cap:] == -7) and np.all(err[cap:] == -7) and np.all(data[cap:] == 0xEE)
+    assert list(chan[:cap]) == [0, 0, 0, 1] and np.all(err[:cap] >= 0)
+    for i in range(cap):
+        assert np.array_equal(data[i], pl[i % 3])
+    fec, dec = bank.fec_counters()
+    assert list(fec) == [3] * nchan and list(dec) == [3] * nchan
+    bank.close()
+    assert C_int32 is nf
