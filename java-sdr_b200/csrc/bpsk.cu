@@ -977,12 +977,13 @@ int launch_scout(jsdr_bpsk *b, jsdr_bpsk::TunerPlan &P, int S)
     static int scout_smem = 0;
     if (!scout_smem) scout_smem = env_int("JSDR_SCOUT_SMEM_KB", 1, 200, kScoutSmem / 1024) * 1024;
     static PerDeviceFlag attr_done;
-    if (!attr_done.test_and_set(ctx->device)) {
+    JSDR_TRY(attr_done.once(ctx->device, [&]() -> int {
         JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
         JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
         JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
         JSDR_CUDA(cudaFuncSetAttribute(k_tuner_scout<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, scout_smem));
-    }
+        return JSDR_OK;
+    }));
     const int per_cta = st * cpt;
     const int grid = (b->nchan + per_cta - 1) / per_cta;
     void (*kern)(const ScoutChan *, const double *, double *, double *, int, int) =
@@ -1075,8 +1076,10 @@ int launch_stream_shape(jsdr_bpsk *b, const stream::Params &sp)
     auto kern = stream::k_mixdecim_stream<FMT, PREC, NTAPS, DD, W>;
     constexpr size_t smem = stream::smem_bytes<FMT, W, DD>();
     static PerDeviceFlag attr_done;
-    if (!attr_done.test_and_set(ctx->device))
+    JSDR_TRY(attr_done.once(ctx->device, [&]() -> int {
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return JSDR_OK;
+    }));
     const int warps = sp.ncw * sp.nseg;
     const int grid = std::min((warps + W - 1) / W, sp.grid);
     JSDR_CUDA(cudaMemsetAsync(sp.work_counter, 0, sizeof(unsigned), ctx->stream));
@@ -1094,8 +1097,10 @@ int launch_pring_shape(jsdr_bpsk *b, const stream::Params &sp)
     auto kern = stream::k_mixdecim_pring<PREC, NTAPS, DD>;
     constexpr size_t smem = stream::p_smem_bytes<DD>();
     static PerDeviceFlag attr_done;
-    if (!attr_done.test_and_set(ctx->device))
+    JSDR_TRY(attr_done.once(ctx->device, [&]() -> int {
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return JSDR_OK;
+    }));
     const int warps = sp.ncw * sp.nseg;
     const int grid = std::min((warps + W - 1) / W, sp.grid);
     JSDR_CUDA(cudaMemsetAsync(sp.work_counter, 0, sizeof(unsigned), ctx->stream));
@@ -1392,8 +1397,10 @@ int bpsk_receive(jsdr_bpsk *b, const void *in, int S, long long chan_stride, int
         dim3 grid((NO + kDm2Tile - 1) / kDm2Tile, nchan);
         const size_t dm_smem = sizeof(double2) * (size_t)(kDm2Tile + 64 + 16);
         static PerDeviceFlag dm_attr;
-        if (!dm_attr.test_and_set(ctx->device))
+        JSDR_TRY(dm_attr.once(ctx->device, [&]() -> int {
             JSDR_CUDA(cudaFuncSetAttribute(k_matched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm_smem));
+            return JSDR_OK;
+        }));
         {
             ProfScope prof(ctx, JSDR_K_MATCHED, ctx->stream);
             k_matched<<<grid, kDm2Threads, dm_smem, ctx->stream>>>(dp);

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <exception>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -96,14 +98,27 @@ namespace jsdr {
 // a launch site is indexed by the context's device, so that contexts on different GPUs of one
 // process each set their own.
 constexpr int kMaxDevices = 64;
+// Contexts on different GPUs may be driven from different threads at the same time (the header's
+// threading rule), so first-use initialisation is serialised: whoever comes second waits until the
+// first has FINISHED (a flag set before the work would let the second thread launch a kernel whose
+// shared-memory limit or constant tables are not there yet).
 struct PerDeviceFlag {
-    bool done[kMaxDevices] = {false};
-    bool test_and_set(int dev)
+    std::mutex mu;
+    std::atomic<bool> done[kMaxDevices];
+    PerDeviceFlag()
     {
-        if (dev < 0 || dev >= kMaxDevices) return false;   // unknown device: redo every time
-        const bool was = done[dev];
-        done[dev] = true;
-        return was;
+        for (auto &d : done) d.store(false, std::memory_order_relaxed);
+    }
+    template <class F>
+    int once(int dev, F &&init)                            // init() -> JSDR status; repeated until it succeeds
+    {
+        const bool known = dev >= 0 && dev < kMaxDevices;  // unknown device: redo every time
+        if (known && done[dev].load(std::memory_order_acquire)) return JSDR_OK;
+        std::lock_guard<std::mutex> lock(mu);
+        if (known && done[dev].load(std::memory_order_relaxed)) return JSDR_OK;
+        const int rc = init();
+        if (rc == JSDR_OK && known) done[dev].store(true, std::memory_order_release);
+        return rc;
     }
 };
 

@@ -482,15 +482,17 @@ try {
     // generated tables and the parity map: once per device, then read-only
     static PerDeviceFlag tables_done;
     static uint8_t *d_rs_par[64] = {nullptr};
-    if (!tables_done.test_and_set(ctx->device)) {
+    JSDR_TRY(tables_done.once(ctx->device, [&]() -> int {
         fec::Tables t;
         fec::build_tables(t);
         JSDR_CUDA(cudaMemcpyToSymbol(fec::c_tab, &t, sizeof(t)));
         uint8_t par[128][fec::NROOTS];
         fec::build_rs_parity_map(t, par);
-        JSDR_CUDA(cudaMalloc(&d_rs_par[ctx->device & 63], sizeof(par)));
+        if (!d_rs_par[ctx->device & 63]) JSDR_CUDA(cudaMalloc(&d_rs_par[ctx->device & 63], sizeof(par)));
         JSDR_CUDA(cudaMemcpy(d_rs_par[ctx->device & 63], par, sizeof(par), cudaMemcpyHostToDevice));
-    }
+        JSDR_CUDA(cudaDeviceSynchronize());        // tables are in place before anyone's kernel reads them
+        return JSDR_OK;
+    }));
     if (b->fec) {                                               // metric table refreshed, state kept: behind this bank's own work
         JSDR_CUDA(cudaMemcpyAsync(b->fec->d_mettab, mettab, 512 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->aux));
         JSDR_CUDA(cudaStreamSynchronize(ctx->aux));
@@ -545,8 +547,10 @@ int jsdr_fec_after_bits(jsdr_bpsk *b)
     }
     const size_t smem = sizeof(fec::DecodeSmem);
     static PerDeviceFlag attr_done;
-    if (!attr_done.test_and_set(ctx->device))
+    JSDR_TRY(attr_done.once(ctx->device, [&]() -> int {
         JSDR_CUDA(cudaFuncSetAttribute(fec::k_fec_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return JSDR_OK;
+    }));
     {
         ProfScope prof(ctx, JSDR_K_FEC, ctx->aux);
         fec::k_fec_decode<<<f->max_frames, 32, smem, ctx->aux>>>(f->d_hist[f->cur], b->d_bits, max_bits, f->d_frames,

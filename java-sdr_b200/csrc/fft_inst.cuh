@@ -18,8 +18,10 @@ static int launch_one(jsdr_ctx *ctx, const Args &a, cudaStream_t st)
     // JSDR_FFT_EXTRA_SMEM_KB: unused shared memory added to every CTA (occupancy experiments only)
     static const size_t extra = []() { const char *e = getenv("JSDR_FFT_EXTRA_SMEM_KB"); return e ? (size_t)std::max(0, atoi(e)) * 1024 : (size_t)0; }();
     const size_t smem = std::min(P::SMEM + extra, (size_t)227 * 1024);
-    if (!attr_done.test_and_set(ctx->device))
+    JSDR_TRY(attr_done.once(ctx->device, [&]() -> int {
         JSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return JSDR_OK;
+    }));
     int grid = (a.nblocks + P::G - 1) / P::G;
     if (grid <= 0) return JSDR_OK;
     static int per_sm = 0;                        // a property of the kernel and sm_100a, not of the device index
