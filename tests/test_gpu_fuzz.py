@@ -522,3 +522,76 @@ def test_frame_capacity_overflow_is_counted_not_written(ctx):
     assert list(fec) == [3] * nchan and list(dec) == [3] * nchan
     bank.close()
     assert C_int32 is nf
+
+
+@pytest.mark.parametrize("seed", range(max(1, int(os.environ.get("JSDR_FUZZ_SEEDS", "24")) // 3)))
+def test_many_handles_interleaved_on_one_context(ctx, seed):
+    """Handles of one context share its streams and fork / join events: several banks (tile and
+    streaming kernel, with and without the frame stage, asynchronous reads), spectrum handlers and
+    a demod called in a drawn order, per-kernel profiling switched on and off in between — every
+    handle still equals its own oracle, as if it were alone."""
+    from test_gpu_parity import check_psd
+    rng = np.random.default_rng(41000 + seed)
+    rate = int(rng.choice([96000, 192000]))
+    n = rate // 10
+    adsc = J.AudioDescriptor(rate)
+    banks = []
+    for _ in range(int(rng.integers(2, 5))):
+        nchan = int(rng.choice([1, 2, 33, 64]))
+        tuning = rng.uniform(-rate / 2.2, rate / 2.2, nchan)
+        b = J.FUNcubeBPSKDemod(ctx, None, adsc, tuning=tuning, stages=int(rng.choice([1, 3, 3])))
+        watch = sorted({0, nchan - 1})
+        banks.append((b, nchan, {c: O.Bpsk(rate, float(tuning[c]), stages=b.stages) for c in watch}))
+    ffts = [J.fft(ctx, None, adsc, max_batch=3, n=int(m)) for m in rng.choice([1024, 4096, n], 2)]
+    d = J.demod(ctx, adsc, nchan=2, max_block=n, dofir=True, dodwn=False)
+    d.weights(2000, 9000)
+    d.weights(-9000, -2000, chan=1)
+    od = [O.Demod(rate, True, False), O.Demod(rate, True, False)]
+    od[0].weights(2000, 9000)
+    od[1].weights(-9000, -2000)
+    pinned = ctx.host_alloc((64 * (n // (rate // 9600) + 2) * 2,), np.float64)
+    profiling = False
+    for step in range(int(rng.integers(8, 20))):
+        if rng.integers(0, 4) == 0:
+            profiling = not profiling
+            ctx.profile(profiling)
+            if not profiling:
+                ctx.profile_read()
+        kind = int(rng.integers(0, 4))
+        if kind <= 1:
+            b, nchan, orcs = banks[int(rng.integers(0, len(banks)))]
+            m = int(rng.choice([n, n, n // 2, 777]))
+            x = rng.uniform(-1, 1, (nchan, 2 * m)).astype(np.float32)
+            b.receive(x, shared=False)
+            if rng.integers(0, 2):
+                nds = b.read_ds_async(pinned)
+                ctx.sync()
+                ds = pinned[:nchan * nds * 2].reshape(nchan, nds, 2).copy()
+            else:
+                ds = b.read_ds()
+            for c, o in orcs.items():
+                r = o.receive(x[c])
+                assert np.array_equal(ds[c], r["ds"]), (seed, step, c)
+                if b.stages == 3:
+                    assert np.array_equal(b.read_bits()[0][c], r["bits"]), (seed, step, c)
+        elif kind == 2:
+            f = ffts[int(rng.integers(0, 2))]
+            batch = int(rng.integers(1, 4))
+            x = rng.uniform(-1, 1, (batch, 2 * f.n)).astype(np.float32)
+            psd, _ = f.receive_batch(x)
+            for k in range(batch):
+                check_psd(psd[k], x[k], rate, f.n)
+        else:
+            m = int(rng.integers(1, n + 1))
+            x = rng.uniform(-1, 1, (2, 2 * m)).astype(np.float32)
+            y = d.receive(x)
+            for c in range(2):
+                assert np.array_equal(y[c], od[c].receive(x[c])), (seed, step, c)
+    ctx.profile(False)
+    ctx.profile_read()
+    ctx.host_free(pinned)
+    for b, _, _ in banks:
+        b.close()
+    for f in ffts:
+        f.close()
+    d.close()
