@@ -71,7 +71,8 @@ int         jsdr_ctx_launch_count(jsdr_ctx *ctx, int64_t *count);
 /* Optional per-kernel timing: while enabled, every launch of the kernels below is
  * bracketed by CUDA events on its own stream; _read waits for the work and returns
  * the summed milliseconds and launch counts per kind since the last read
- * (ms/count hold JSDR_K_COUNT entries).  bench.py's roofline numbers come from here. */
+ * (ms/count hold JSDR_K_COUNT entries; at most 65536 launches are kept between two reads,
+ * later ones are not timed).  bench.py's roofline numbers come from here. */
 enum { JSDR_K_FFT = 0, JSDR_K_MIXDECIM = 1, JSDR_K_MATCHED = 2, JSDR_K_TIMING = 3, JSDR_K_SCOUT = 4,
        JSDR_K_OTHER = 5, JSDR_K_DEMOD = 6, JSDR_K_FIR = 7, JSDR_K_DETECT = 8, JSDR_K_WATERFALL = 9,
        JSDR_K_SYNC = 10, JSDR_K_FEC = 11, JSDR_K_COUNT = 12 };

@@ -147,6 +147,10 @@ try {
 extern "C" int jsdr_ctx_profile(jsdr_ctx *ctx, int enable)
 try {
     JSDR_REQUIRE(ctx, JSDR_EINVAL, "null argument");
+    if (enable) {                                   // room for every span up front: recording never allocates
+        ctx->spans.reserve(jsdr::kMaxProfSpans);
+        ctx->free_spans.reserve(jsdr::kMaxProfSpans);
+    }
     ctx->profiling = enable != 0;
     return JSDR_OK;
 } JSDR_CATCH_ALL

@@ -134,21 +134,26 @@ static inline int launched(jsdr_ctx *ctx, const char *what)
     return JSDR_OK;
 }
 
-// Bracket one kernel launch with CUDA events on its stream when profiling is on.
+// Bracket one kernel launch with CUDA events on its stream when profiling is on.  At most
+// kMaxProfSpans launches are kept between two reads (a caller that switches profiling on and never
+// reads must not grow event pairs without bound); later launches are simply not timed.
+constexpr size_t kMaxProfSpans = 1 << 16;
 struct ProfScope {
     jsdr_ctx *ctx;
     cudaStream_t st;
     jsdr_prof_span sp;
     bool on;
-    ProfScope(jsdr_ctx *c, int kind, cudaStream_t s) : ctx(c), st(s), on(c->profiling)
+    ProfScope(jsdr_ctx *c, int kind, cudaStream_t s)
+        : ctx(c), st(s), on(c->profiling && c->spans.size() < kMaxProfSpans && c->spans.size() < c->spans.capacity())
     {
         if (!on) return;
         if (!c->free_spans.empty()) {
             sp = c->free_spans.back();
             c->free_spans.pop_back();
-        } else {
-            cudaEventCreate(&sp.a);
-            cudaEventCreate(&sp.b);
+        } else if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) {
+            cudaGetLastError();
+            on = false;
+            return;
         }
         sp.kind = kind;
         cudaEventRecord(sp.a, st);

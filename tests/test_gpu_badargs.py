@@ -150,3 +150,32 @@ def test_bad_arguments_on_live_handles(ctx):
             assert np.array_equal(x, y)
     for h in (f, b, d, r):
         h.close()
+
+
+def test_profiling_left_on_and_never_read_is_bounded(ctx):
+    """Switch per-kernel timing on, launch 70 000 kernels without ever reading: at most 65 536
+    spans (event pairs) are kept, the rest simply is not timed, results are unaffected and the
+    next read starts afresh."""
+    n = 128
+    f = J.fft(ctx, None, J.AudioDescriptor(44100, blen=4 * n), max_batch=1, n=n)
+    d_in, d_psd = ctx.dev_alloc(8 * n), ctx.dev_alloc(4 * (n + 2))
+    x = np.random.default_rng(0).uniform(-1, 1, 2 * n).astype(np.float32)
+    d_in.upload(x)
+    want = f.receive(x).copy()
+    ctx.profile(True)
+    for _ in range(70000):
+        f.receive_dev(d_in.ptr, 1, d_psd.ptr, None, s16=False)
+    prof = ctx.profile_read()
+    total = sum(int(v[1]) for v in prof.values()) if isinstance(next(iter(prof.values())), (tuple, list)) else None
+    L = J.lib()
+    ms, cnt = np.zeros(12), np.zeros(12, np.int64)
+    f.receive_dev(d_in.ptr, 1, d_psd.ptr, None, s16=False)
+    assert L.jsdr_ctx_profile_read(ctx.h, p(ms), p(cnt), 12) == 0
+    assert cnt.sum() == 1 and cnt[0] == 1                     # afresh: exactly the one launch since the read
+    if total is not None:
+        assert total == 65536, total
+    ctx.profile(False)
+    assert np.array_equal(d_psd.download(np.float32, n + 2), want)
+    d_in.free()
+    d_psd.free()
+    f.close()
