@@ -94,23 +94,71 @@ def synth_tile(nchan, S, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+    NVML from a thread of this process every ~4 ms (no start-up delay, so even a 150 ms region
+    gets dozens of samples); `nvidia-smi -lms 20` is the fall-back when NVML cannot be loaded,
+    and then start() waits for its first row (a fresh box can take seconds to produce it)."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.nvml, self.th = device, [], None, None, None
+        self.source = None
+        self._stop = threading.Event()
+
+    @staticmethod
+    def physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if local < len(ids) and ids[local].isdigit():
+            return int(ids[local])
+        return local
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.physical_index(self.device))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.source = pynvml, "nvml"
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.device)],
+                                          "-lms", "20", "-i", str(self.physical_index(self.device))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t_end = time.time() + 15.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                r = ["", sm, self.mx, "", ""] + ["Active" if mask & bit else "Not Active" for _, bit in names]
+                self.rows.append((time.time(), r))
+            except Exception:
+                pass
+            self._stop.wait(0.004)
 
     def _read(self):
         import datetime
@@ -127,23 +175,27 @@ class ClockSampler:
         self.t0, self.t1 = t0 - 0.03, t1 + 0.03
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        try:
+        if self.nvml is not None:
+            self._stop.set()
             self.th.join(timeout=1.0)
-        except Exception:
-            pass
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            try:
+                self.th.join(timeout=1.0)
+            except Exception:
+                pass
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML and no nvidia-smi on this host"]}
         sm, mx, reasons = [], [], set()
         t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
         rows = [(ts, r) for ts, r in self.rows if t0 is None or t0 <= ts <= t1]
         scope = "timed region"
-        if len(rows) < 3:   # too short a region for nvidia-smi's sampling period: everything since before the warm-up
+        if len(rows) < 3:   # too short a region for the sampling period: everything since before the warm-up
             rows, scope = self.rows, "warm-up + timed region"
         for ts, r in rows:
             try:
@@ -151,10 +203,10 @@ class ClockSampler:
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "source": self.source, "reasons": sorted(reasons)}
 
 
 def cpu_pipeline(a, seconds, nthreads):
