@@ -155,6 +155,20 @@ __device__ __forceinline__ float2 cmul_w(float2 a)
 }
 
 // ------------------------------------------------------------------ register DFTs
+// Constant twiddles are never multiplied out.  Every register DFT exists in the form
+// run_tw<K, RR>: the DFT of v[n] * w^n with w = exp(-2*pi*i*K/RR) (run = run_tw<0, R>).  A
+// composite length hands its internal twiddles W_R^(n2*k1) down as the K of its sub-transforms
+// (they are geometric in n2), so they all arrive at radix-2 / radix-4 butterflies of the form
+// a +- w*b, which cost THREE packed instructions instead of four (cmul + add + sub):
+//   w = c*(1 + i*t):  u = b + t*(i*b);  a + c*u;  a - c*u        (|c| >= |s|, t = s/c)
+//   w = s*(i + t'):   u = i*b + t'*b;   a + s*u;  a - s*u        (otherwise,  t' = c/s)
+// (the multiply-add form of Linzer & Feig / Goedecker).  A 64-point DFT is 482 packed
+// instructions this way against 546 with the twiddles multiplied out; JSDR_FFT_FUSED_TW=0
+// builds the multiplied-out form for comparison.
+#ifndef JSDR_FFT_FUSED_TW
+#define JSDR_FFT_FUSED_TW 1
+#endif
+
 constexpr int pick_factor(int r)
 {
     if (r % 4 == 0) return 4;
@@ -164,43 +178,94 @@ constexpr int pick_factor(int r)
     return r;
 }
 constexpr bool is_base(int r) { return r == 1 || r == 2 || r == 4 || (r % 2 == 1 && pick_factor(r) == r); }
+__host__ __device__ constexpr int mod_pos(int k, int r) { return ((k % r) + r) % r; }
+__host__ __device__ constexpr double cx_abs(double x) { return x < 0 ? -x : x; }
+
+// plus = a + w*b, minus = a - w*b, w = exp(-2*pi*i*K/RR)
+template <int K, int RR>
+__device__ __forceinline__ void bfly_tw(float2 a, float2 b, float2 &plus, float2 &minus)
+{
+    constexpr int k = mod_pos(K, RR);
+    if constexpr (k == 0) {
+        plus = cadd(a, b);
+        minus = csub(a, b);
+    } else if constexpr (4 * k == RR) {            // w = -i
+        plus = cadd(a, mul_mi(b));
+        minus = csub(a, mul_mi(b));
+    } else if constexpr (2 * k == RR) {            // w = -1
+        plus = csub(a, b);
+        minus = cadd(a, b);
+    } else if constexpr (4 * k == 3 * RR) {        // w = +i
+        plus = cadd(a, mul_pi(b));
+        minus = csub(a, mul_pi(b));
+    } else {
+        constexpr double c = cx_cos2pi(k, RR), s = -cx_sin2pi(k, RR);     // w = c + i*s
+        if constexpr (cx_abs(c) >= cx_abs(s)) {
+            constexpr float t = (float)(s / c), cf = (float)c;
+            const float2 u = pfma(mul_pi(b), bcast(t), b);                 // b + t*(i*b)
+            plus = pfma(u, bcast(cf), a);
+            minus = pfma(u, bcast(-cf), a);
+        } else {
+            constexpr float t = (float)(c / s), sf = (float)s;
+            const float2 u = pfma(b, bcast(t), mul_pi(b));                 // i*b + t*b
+            plus = pfma(u, bcast(sf), a);
+            minus = pfma(u, bcast(-sf), a);
+        }
+    }
+}
 
 template <int R, bool BASE = is_base(R)>
 struct Dft;
 
 template <>
 struct Dft<1, true> {
+    template <int K, int RR>
+    static __device__ __forceinline__ void run_tw(float2 *) {}
     static __device__ __forceinline__ void run(float2 *) {}
 };
 
 template <>
 struct Dft<2, true> {
-    static __device__ __forceinline__ void run(float2 *v)
+    template <int K, int RR>
+    static __device__ __forceinline__ void run_tw(float2 *v)
     {
         float2 a = v[0], b = v[1];
-        v[0] = cadd(a, b);
-        v[1] = csub(a, b);
+        bfly_tw<K, RR>(a, b, v[0], v[1]);
     }
+    static __device__ __forceinline__ void run(float2 *v) { run_tw<0, 2>(v); }
 };
 
 template <>
 struct Dft<4, true> {
-    static __device__ __forceinline__ void run(float2 *v)
+    // inputs u0, w*u1, w^2*u2, w^3*u3:  a0,a1 = u0 +- w^2*u2;  s,d = u1 +- w^2*u3;
+    // X0,X2 = a0 +- w*s;  X1,X3 = a1 +- (-i*w)*d
+    template <int K, int RR>
+    static __device__ __forceinline__ void run_tw(float2 *v)
     {
-        float2 a0 = cadd(v[0], v[2]);
-        float2 a1 = csub(v[0], v[2]);
-        float2 a2 = cadd(v[1], v[3]);
-        float2 a3 = mul_mi(csub(v[1], v[3]));   // -i*(v1 - v3), folded into the consumers
-        v[0] = cadd(a0, a2);
-        v[1] = cadd(a1, a3);
-        v[2] = csub(a0, a2);
-        v[3] = csub(a1, a3);
+        static_assert(RR % 4 == 0, "radix 4 inside a length that 4 does not divide");
+        float2 a0, a1, s, d;
+        bfly_tw<2 * K, RR>(v[0], v[2], a0, a1);
+        bfly_tw<2 * K, RR>(v[1], v[3], s, d);
+        bfly_tw<K, RR>(a0, s, v[0], v[2]);
+        bfly_tw<K + RR / 4, RR>(a1, d, v[1], v[3]);
     }
+    static __device__ __forceinline__ void run(float2 *v) { run_tw<0, 4>(v); }
 };
 
 // odd prime P: pair x[n] with x[P-n]
 template <int P>
 struct Dft<P, true> {
+    template <int K, int RR>
+    static __device__ __forceinline__ void run_tw(float2 *v)
+    {
+        if constexpr (mod_pos(K, RR) != 0) {
+            static_for<1, P>([&](auto nn) {
+                constexpr int n = decltype(nn)::value;
+                v[n] = cmul_w<K * n, RR>(v[n]);
+            });
+        }
+        run(v);
+    }
     static __device__ __forceinline__ void run(float2 *v)
     {
         constexpr int H = (P - 1) / 2;
@@ -238,8 +303,40 @@ template <int R>
 struct Dft<R, false> {
     static constexpr int A = pick_factor(R);
     static constexpr int B = R / A;
-    static __device__ __forceinline__ void run(float2 *v)
+    // DFT of v[n] * w^n, w = exp(-2*pi*i*K/RR): w^n = (w^B)^n1 * w^n2; the first factor is the
+    // twiddle progression of the length-A transforms, the second joins the internal twiddle
+    // W_R^(n2*k1) = exp(-2*pi*i*n2*k1*(RR/R)/RR) as the progression of the length-B ones
+    template <int K, int RR>
+    static __device__ __forceinline__ void run_tw(float2 *v)
     {
+#if JSDR_FFT_FUSED_TW
+        static_assert(RR % R == 0, "sub-transform length divides the outer one");
+        float2 t[R];
+        static_for<0, B>([&](auto nn2) {
+            constexpr int n2 = decltype(nn2)::value;
+            float2 a[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; n1++) a[n1] = v[B * n1 + n2];
+            Dft<A>::template run_tw<mod_pos(K * B, RR), RR>(a);
+#pragma unroll
+            for (int k1 = 0; k1 < A; k1++) t[k1 * B + n2] = a[k1];
+        });
+        static_for<0, A>([&](auto kk1) {
+            constexpr int k1 = decltype(kk1)::value;
+            float2 b[B];
+#pragma unroll
+            for (int n2 = 0; n2 < B; n2++) b[n2] = t[k1 * B + n2];
+            Dft<B>::template run_tw<mod_pos(K + k1 * (RR / R), RR), RR>(b);
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) v[k1 + A * k2] = b[k2];
+        });
+#else
+        if constexpr (mod_pos(K, RR) != 0) {
+            static_for<1, R>([&](auto nn) {
+                constexpr int n = decltype(nn)::value;
+                v[n] = cmul_w<K * n, RR>(v[n]);
+            });
+        }
         float2 t[R];
         static_for<0, B>([&](auto nn2) {
             constexpr int n2 = decltype(nn2)::value;
@@ -261,7 +358,9 @@ struct Dft<R, false> {
 #pragma unroll
             for (int k2 = 0; k2 < B; k2++) v[k1 + A * k2] = b[k2];
         }
+#endif
     }
+    static __device__ __forceinline__ void run(float2 *v) { run_tw<0, R>(v); }
 };
 
 // v[r] *= w1^r for r = 1..R-1, powers by a balanced product tree (depth log2 R)
