@@ -32,7 +32,10 @@ namespace jsdr {
 namespace bpsk {
 namespace stream {
 
-constexpr int kWarps = 16;            // s16 input: 16 warps (one CTA per SM: 231552 B of shared memory, 128 registers)
+#ifndef JSDR_STREAM_WARPS
+#define JSDR_STREAM_WARPS 16
+#endif
+constexpr int kWarps = JSDR_STREAM_WARPS;   // s16 input: 16 warps (one CTA per SM: 231552 B of shared memory, 128 registers); the macro is an occupancy probe
 constexpr int kWarpsF32 = 8;          // float input: the ring rows are twice as wide
 constexpr int kMaxTaps = 64;
 enum { PREC_F64 = 0, PREC_F32 = 1 };
