@@ -168,7 +168,7 @@ constexpr int kScoutThreads = 512;   // launch bound; the CTA size in use is sco
 constexpr int kScoutMaxCpt = 4;
 // Dynamic shared memory a scout CTA asks for (and never uses): more than half an SM's 227 KB, so
 // that two scout CTAs can never share an SM (at 90 KB two did when an SM emptied -- a 1024-channel
-// bank ran its replay in 7.4 ms instead of 6.0); what is left still takes one 67.6 KB CTA of
+// bank ran its replay in 7.4 ms instead of 6.0); what is left still takes three 33.8 KB CTAs of
 // the N = 4096 FFT plan beside it.  JSDR_SCOUT_SMEM_KB overrides it (tuning aid).
 constexpr int kScoutSmem = 116 * 1024;
 

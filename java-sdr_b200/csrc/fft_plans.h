@@ -9,7 +9,7 @@
     X(512, 256, 8, 32, 16, 1, 1)     \
     X(1024, 256, 8, 32, 32, 1, 1)    \
     X(2048, 128, 1, 16, 8, 16, 1)    \
-    X(4096, 128, 2, 64, 64, 1, 1)    \
+    X(4096, 64, 1, 64, 64, 1, 1)    \
     X(8192, 256, 1, 32, 16, 16, 1)   \
     X(16384, 512, 1, 32, 32, 16, 1)  \
     X(4410, 224, 1, 10, 21, 21, 1)   \
