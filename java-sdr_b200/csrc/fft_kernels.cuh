@@ -428,6 +428,17 @@ struct Plan {
     static constexpr int MINB_REGS = 65536 / (T_ * REG_BUDGET);
     static constexpr int MINB_FIT = (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS) < 1 ? 1 : (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS);
     static constexpr int MINB = (RMAX > 32 || (RMAX & (RMAX - 1)) != 0 || PERSIST) ? 0 : MINB_FIT;
+    // Persistent plans keep the twiddle bases of every pass in shared memory behind the block (the
+    // block leaves room: one CTA per SM): R0 values for the first middle pass, R0*R1 for the
+    // second, ML for the last -- a shared-memory load where every butterfly waited for L2.
+#ifndef JSDR_FFT_TW_SMEM
+#define JSDR_FFT_TW_SMEM 1
+#endif
+    static constexpr int TW1 = (K >= 3) ? R0_ : 0;
+    static constexpr int TW2 = (K >= 4) ? R0_ * R1_ : 0;
+    static constexpr int TW_ELEMS = TW1 + TW2 + ML;
+    static constexpr bool TW_SMEM = JSDR_FFT_TW_SMEM && PERSIST && (SMEM + TW_ELEMS * sizeof(float2) + 2048 <= 227 * 1024);
+    static constexpr size_t SMEM_PERSIST = SMEM + (TW_SMEM ? TW_ELEMS * sizeof(float2) : 0);
     static constexpr bool PACK_IN = true;
     static constexpr bool GROUP_IN = true;
     static constexpr int NB0 = N_ / R0_;
@@ -527,7 +538,7 @@ __device__ __forceinline__ void load_strided(float2 *v, const float2 *p)
 }
 
 // middle pass p: sub-transform length L = M*R, butterfly stride M
-template <class P, int R, int M>
+template <class P, int R, int M, bool TWS = false>
 __device__ __forceinline__ void middle_pass(float2 *sm, const float2 *__restrict__ tw, int tid)
 {
     constexpr int L = M * R;
@@ -539,7 +550,9 @@ __device__ __forceinline__ void middle_pass(float2 *sm, const float2 *__restrict
         float2 *p = sm + g * P::FFT_ELEMS + lin + (lin / P::ML) * P::PAD;
         float2 v[R];
         load_strided<R, M>(v, p);
-        float2 w1 = __ldg(tw + j * (P::N / L));
+        float2 w1;
+        if constexpr (TWS) w1 = tw[j];            // shared-memory copy of tw[j * N/L], j < M
+        else w1 = __ldg(tw + j * (P::N / L));
         twiddle_powers<R>(v, w1);
         Dft<R>::run(v);
 #pragma unroll
@@ -570,7 +583,17 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
     // persistent only where the register prefetch exists (s16 input: one register per sample);
     // float input keeps one CTA per block and the L2 prefetch (measured: 0.50 -> 0.61 at 16384)
     constexpr bool PERSIST = P::PERSIST && IN == IN_S16 && SPLIT == 1;
-    constexpr bool PREFETCH = PERSIST;
+    // Register prefetch only where one round of pass 0 covers the block (PRE_IT = 1: 16384).  With
+    // two rounds (19200: 2 x 16 values beside the butterflies at a 96-register budget) the compiler
+    // keeps pre[] in LOCAL memory, and the store that spills a value waits for its load: the
+    // "prefetch" stalled every warp in front of the last pass (ncu source page: STL, long scoreboard,
+    // 8 % of all stall samples).  Those plans ask for the next block with one bulk L2 prefetch
+    // instead, as the non-persistent plans do, and load pass 0 from L2.
+#ifndef JSDR_FFT_REGPF_MAX_IT
+#define JSDR_FFT_REGPF_MAX_IT 1
+#endif
+    constexpr bool PREFETCH = PERSIST && (P::PRE_IT <= JSDR_FFT_REGPF_MAX_IT);
+    constexpr bool L2_NEXT = PERSIST && !PREFETCH;
 
     // pass-0 samples of the next block (persistent plans, s16 input)
     uint32_t pre[PREFETCH ? P::PRE_IT : 1][PREFETCH ? P::R0 : 1];
@@ -589,6 +612,18 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
     };
     if constexpr (PREFETCH) {
         if ((long)blockIdx.x < a.nblocks) prefetch(blockIdx.x);
+    }
+
+    constexpr bool TWS = P::TW_SMEM && PERSIST;
+    float2 *tw_s1 = sm + P::G * P::FFT_ELEMS;      // [TW1]  tw[j * N/(R0*R1)]
+    float2 *tw_s2 = tw_s1 + P::TW1;                // [TW2]  tw[j * N/(R0*R1*R2)]
+    float2 *tw_sl = tw_s2 + P::TW2;                // [ML]   tw[j]
+    if constexpr (TWS) {
+        for (int i = tid; i < P::TW1; i += P::T) tw_s1[i] = __ldg(a.tw + i * (N / (P::R0 * P::R1)));
+        if constexpr (P::K >= 4)
+            for (int i = tid; i < P::TW2; i += P::T) tw_s2[i] = __ldg(a.tw + i * (N / (P::R0 * P::R1 * P::R2)));
+        for (int i = tid; i < P::ML; i += P::T) tw_sl[i] = __ldg(a.tw + i);
+        // (visible to every thread after the barrier that follows pass 0)
     }
 
     // one pass for ordinary plans (a CTA owns blocks blk0 .. blk0+G-1); persistent plans loop
@@ -615,6 +650,13 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
         }
     }
     do {
+    if constexpr (L2_NEXT) {
+        if (tid == 0 && blk0 + blk_step < a.nblocks) {
+            const size_t lo = (reinterpret_cast<size_t>(a.in) + (size_t)(blk0 + blk_step) * N * 4 + 15) & ~(size_t)15;
+            const size_t hi = (reinterpret_cast<size_t>(a.in) + (size_t)(blk0 + blk_step + 1) * N * 4) & ~(size_t)15;
+            if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+        }
+    }
 
     // Plans whose blocks keep the same warp in every pass (two passes, NB0 == ML == 32: N = 1024)
     // never exchange data between warps: warp convergence replaces the CTA barrier at every pass
@@ -746,11 +788,13 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 
     // ---------------- middle passes (in place)
     if constexpr (P::K >= 3) {
-        middle_pass<P, P::R1, P::R0>(sm, a.tw, tid);
+        if constexpr (TWS) middle_pass<P, P::R1, P::R0, true>(sm, tw_s1, tid);
+        else middle_pass<P, P::R1, P::R0>(sm, a.tw, tid);
         __syncthreads();
     }
     if constexpr (P::K >= 4) {
-        middle_pass<P, P::R2, P::R0 * P::R1>(sm, a.tw, tid);
+        if constexpr (TWS) middle_pass<P, P::R2, P::R0 * P::R1, true>(sm, tw_s2, tid);
+        else middle_pass<P, P::R2, P::R0 * P::R1>(sm, a.tw, tid);
         __syncthreads();
     }
 
@@ -786,7 +830,9 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
             const float2 *p = sm + g * P::FFT_ELEMS + j;
 #pragma unroll
             for (int r = 0; r < RL; r++) v[r] = p[r * P::PITCH];
-            float2 w1 = __ldg(a.tw + j);
+            float2 w1;
+            if constexpr (TWS) w1 = tw_sl[j];
+            else w1 = __ldg(a.tw + j);
             twiddle_powers<RL>(v, w1);
             Dft<RL>::run(v);
             // where this (half) block's bin k goes: bin SPLIT*k + h of block blk / SPLIT
