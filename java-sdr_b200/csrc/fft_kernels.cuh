@@ -594,11 +594,19 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 #endif
     constexpr bool PREFETCH = PERSIST && (P::PRE_IT <= JSDR_FFT_REGPF_MAX_IT);
     constexpr bool L2_NEXT = PERSIST && !PREFETCH;
+    // ... and fetch BOTH rounds of their own pass 0 before the first butterfly (the shared-memory
+    // stores of round one would otherwise hold back the loads of round two): pre[] then lives
+    // only inside pass 0 and stays in registers.
+#ifndef JSDR_FFT_EARLY_LOADS
+#define JSDR_FFT_EARLY_LOADS 1
+#endif
+    constexpr bool EARLY = JSDR_FFT_EARLY_LOADS && L2_NEXT && IN == IN_S16;
+    constexpr bool PRE = PREFETCH || EARLY;
 
     // pass-0 samples of the next block (persistent plans, s16 input)
-    uint32_t pre[PREFETCH ? P::PRE_IT : 1][PREFETCH ? P::R0 : 1];
+    uint32_t pre[PRE ? P::PRE_IT : 1][PRE ? P::R0 : 1];
     auto prefetch = [&](long blk) {
-        if constexpr (PREFETCH) {
+        if constexpr (PRE) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in) + blk * N;
 #pragma unroll
             for (int it = 0; it < P::PRE_IT; it++) {
@@ -682,9 +690,10 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
     {
         constexpr int R0 = P::R0;
         constexpr int NB0 = N / R0;
+        if constexpr (EARLY) prefetch(blk0);
 #pragma unroll
-        for (int it = 0; it < (PREFETCH ? P::PRE_IT : 1); it++) {
-        for (int U = PREFETCH ? tid + it * P::T : tid; U < P::G * NB0; U += PREFETCH ? P::G * NB0 : P::T) {
+        for (int it = 0; it < (PRE ? P::PRE_IT : 1); it++) {
+        for (int U = PRE ? tid + it * P::T : tid; U < P::G * NB0; U += PRE ? P::G * NB0 : P::T) {
             int g = U / NB0, c = U - g * NB0;
             long blk = blk0 + g;
             if (blk >= a.nblocks) continue;
@@ -740,7 +749,7 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                 });
             } else if constexpr (IN == IN_S16 && P::GROUP_IN) {
                 uint32_t w[R0];
-                if constexpr (PREFETCH) {
+                if constexpr (PRE) {
 #pragma unroll
                     for (int m = 0; m < R0; m++) w[m] = pre[it][m];
                 } else {
