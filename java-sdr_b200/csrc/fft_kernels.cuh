@@ -600,7 +600,8 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 #ifndef JSDR_FFT_EARLY_LOADS
 #define JSDR_FFT_EARLY_LOADS 1
 #endif
-    constexpr bool EARLY = JSDR_FFT_EARLY_LOADS && L2_NEXT && IN == IN_S16;
+    constexpr bool EARLY = JSDR_FFT_EARLY_LOADS && IN == IN_S16 && SPLIT == 1 && P::G == 1 && !PREFETCH &&
+                           P::PRE_IT >= 2 && P::PRE_IT * P::R0 <= 40;       // (19200: 2 x 16; 4410: 2 x 10)
     constexpr bool PRE = PREFETCH || EARLY;
 
     // pass-0 samples of the next block (persistent plans, s16 input)
