@@ -1,3 +1,3 @@
 // generated per-length instantiation (see fft_plans.h)
 #include "fft_inst.cuh"
-JSDR_FFT_DEFINE(1024, 256, 8, 32, 32, 1, 1)
+JSDR_FFT_DEFINE(1024, 128, 4, 32, 32, 1, 1)

@@ -1,3 +1,3 @@
 // generated per-length instantiation (see fft_plans.h)
 #include "fft_inst.cuh"
-JSDR_FFT_DEFINE(512, 256, 8, 32, 16, 1, 1)
+JSDR_FFT_DEFINE(512, 64, 4, 16, 32, 1, 1)

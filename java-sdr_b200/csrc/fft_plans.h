@@ -4,10 +4,10 @@
 // odd radices of N = rate/10 (fft.java:67, JavaAudio.java:59) come last.
 #pragma once
 #define JSDR_FFT_PLANS(X)            \
-    X(128, 256, 16, 16, 8, 1, 1)     \
-    X(256, 256, 16, 16, 16, 1, 1)    \
-    X(512, 256, 8, 32, 16, 1, 1)     \
-    X(1024, 256, 8, 32, 32, 1, 1)    \
+    X(128, 64, 8, 8, 16, 1, 1)     \
+    X(256, 128, 8, 16, 16, 1, 1)    \
+    X(512, 64, 4, 16, 32, 1, 1)     \
+    X(1024, 128, 4, 32, 32, 1, 1)    \
     X(2048, 128, 1, 16, 8, 16, 1)    \
     X(4096, 64, 1, 64, 64, 1, 1)    \
     X(8192, 256, 1, 32, 16, 16, 1)   \
