@@ -416,7 +416,10 @@ struct Plan {
 #ifndef JSDR_FFT_NO_PERSIST
 #define JSDR_FFT_NO_PERSIST 0
 #endif
-    static constexpr bool PERSIST = !JSDR_FFT_NO_PERSIST && (G_ == 1) && (N_ >= 9600) && (SMEM > 113 * 1024);   // only one CTA fits an SM
+#ifndef JSDR_FFT_PERSIST_MIN_KB
+#define JSDR_FFT_PERSIST_MIN_KB 113
+#endif
+    static constexpr bool PERSIST = !JSDR_FFT_NO_PERSIST && (G_ == 1) && (N_ >= 9600) && (SMEM > JSDR_FFT_PERSIST_MIN_KB * 1024);   // one CTA per SM (113) or two (70: N = 9600)
     // CTAs per SM the kernel is compiled for: what shared memory allows, at the register budget
     // the largest register DFT needs.  Radix <= 16 fits 48 registers (4096 = 16^3 then keeps five
     // CTAs per SM instead of slipping to four); radix 32 fits 80, and a 256-thread CTA at 81..88
@@ -427,7 +430,7 @@ struct Plan {
     static constexpr int MINB_SMEM = (int)((227 * 1024) / (SMEM + 1024));
     static constexpr int MINB_REGS = 65536 / (T_ * REG_BUDGET);
     static constexpr int MINB_FIT = (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS) < 1 ? 1 : (MINB_SMEM < MINB_REGS ? MINB_SMEM : MINB_REGS);
-    static constexpr int MINB = (RMAX > 32 || (RMAX & (RMAX - 1)) != 0 || PERSIST) ? 0 : MINB_FIT;
+    static constexpr int MINB = PERSIST ? (MINB_SMEM > 1 ? MINB_SMEM : 0) : (RMAX > 32 || (RMAX & (RMAX - 1)) != 0) ? 0 : MINB_FIT;
     // Persistent plans keep the twiddle bases of every pass in shared memory behind the block (the
     // block leaves room: one CTA per SM): R0 values for the first middle pass, R0*R1 for the
     // second, ML for the last -- a shared-memory load where every butterfly waited for L2.
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
 #ifndef JSDR_FFT_REGPF_MAX_IT
 #define JSDR_FFT_REGPF_MAX_IT 1
 #endif
-    constexpr bool PREFETCH = PERSIST && (P::PRE_IT <= JSDR_FFT_REGPF_MAX_IT);
+    constexpr bool PREFETCH = PERSIST && (P::PRE_IT <= JSDR_FFT_REGPF_MAX_IT) && (P::MINB_SMEM < 2);   // (two CTAs per SM: no room for pre[])
     constexpr bool L2_NEXT = PERSIST && !PREFETCH;
     // ... and fetch BOTH rounds of their own pass 0 before the first butterfly (the shared-memory
     // stores of round one would otherwise hold back the loads of round two): pre[] then lives
