@@ -255,7 +255,11 @@ __device__ __forceinline__ void period_body(const Params &p, const typename Raw<
 }
 
 template <int FMT, int PREC, int NTAPS, int DD, int W>
+#ifdef JSDR_STREAM_MAXNREG      // (experiment: leave registers for a co-resident phase-scout warp)
+__global__ void __maxnreg__(JSDR_STREAM_MAXNREG) k_mixdecim_stream(const Params p)
+#else
 __global__ void __launch_bounds__(W * 32, 1) k_mixdecim_stream(const Params p)
+#endif
 {
     typedef typename Raw<FMT>::type raw_t;
     constexpr int NQ = (NTAPS + DD - 1) / DD;          // live outputs per sample
