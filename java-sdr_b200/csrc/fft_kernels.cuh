@@ -442,6 +442,18 @@ struct Plan {
     static constexpr int TW_ELEMS = TW1 + TW2 + ML;
     static constexpr bool TW_SMEM = JSDR_FFT_TW_SMEM && PERSIST && (SMEM + TW_ELEMS * sizeof(float2) + 2048 <= 227 * 1024);
     static constexpr size_t SMEM_PERSIST = SMEM + (TW_SMEM ? TW_ELEMS * sizeof(float2) : 0);
+    // The same tables for the ordinary (one CTA per block) three- and four-pass plans, where they
+    // cost no CTA per SM: each thread fetches its share into registers before pass 0 and stores
+    // it to shared memory behind pass 0, so the fetch hides behind the pass-0 loads.
+#ifndef JSDR_FFT_TW_SMEM_NP
+#define JSDR_FFT_TW_SMEM_NP 1
+#endif
+    static constexpr int TW_PER_THREAD = (TW_ELEMS + T_ - 1) / T_;
+    // (N >= 8192 only: measured +5.7 % at 8192 and +4.3 % at 9600 for s16 input; at 4800 the extra
+    // registers cost a CTA per SM, -8 %, and 2048 / 4410 do not move)
+    static constexpr bool TW_SMEM_NP = JSDR_FFT_TW_SMEM_NP && !PERSIST && G_ == 1 && K >= 3 && N_ >= 8192 && TW_PER_THREAD <= 4 &&
+                                       (int)((227 * 1024) / (SMEM + TW_ELEMS * sizeof(float2) + 1024)) == (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr size_t SMEM_TW = SMEM + TW_ELEMS * sizeof(float2);
     static constexpr bool PACK_IN = true;
     static constexpr bool GROUP_IN = true;
     static constexpr int NB0 = N_ / R0_;
@@ -626,11 +638,26 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
         if ((long)blockIdx.x < a.nblocks) prefetch(blockIdx.x);
     }
 
-    constexpr bool TWS = P::TW_SMEM && PERSIST;
+    constexpr bool TWN = P::TW_SMEM_NP && SPLIT == 1;            // ordinary plans: through registers, see Plan
+    constexpr bool TWP = P::TW_SMEM && PERSIST;
+    constexpr bool TWS = TWP || TWN;
     float2 *tw_s1 = sm + P::G * P::FFT_ELEMS;      // [TW1]  tw[j * N/(R0*R1)]
     float2 *tw_s2 = tw_s1 + P::TW1;                // [TW2]  tw[j * N/(R0*R1*R2)]
     float2 *tw_sl = tw_s2 + P::TW2;                // [ML]   tw[j]
-    if constexpr (TWS) {
+    float2 twr[TWN ? P::TW_PER_THREAD : 1];
+    if constexpr (TWN) {
+#pragma unroll
+        for (int k = 0; k < P::TW_PER_THREAD; k++) {
+            const int i = tid + k * P::T;
+            if (i < P::TW_ELEMS) {
+                const int src = (i < P::TW1) ? i * (N / (P::R0 * P::R1))
+                              : (i < P::TW1 + P::TW2) ? (i - P::TW1) * (N / (P::R0 * P::R1 * (P::K >= 4 ? P::R2 : 1)))
+                              : i - P::TW1 - P::TW2;
+                twr[k] = __ldg(a.tw + src);
+            }
+        }
+    }
+    if constexpr (TWP) {
         for (int i = tid; i < P::TW1; i += P::T) tw_s1[i] = __ldg(a.tw + i * (N / (P::R0 * P::R1)));
         if constexpr (P::K >= 4)
             for (int i = tid; i < P::TW2; i += P::T) tw_s2[i] = __ldg(a.tw + i * (N / (P::R0 * P::R1 * P::R2)));
@@ -795,6 +822,13 @@ __global__ void __launch_bounds__(P::T, P::MINB) fft_kernel(const Args a)
                 asm volatile("st.shared.v2.f32 [%0+%1], {%2,%3};" ::"r"(dst), "n"(m * 8), "f"(v[m].x), "f"(v[m].y) : "memory");
             });
         }
+        }
+    }
+    if constexpr (TWN) {
+#pragma unroll
+        for (int k = 0; k < P::TW_PER_THREAD; k++) {
+            const int i = tid + k * P::T;
+            if (i < P::TW_ELEMS) tw_s1[i] = twr[k];
         }
     }
     block_sync();
