@@ -8,7 +8,7 @@
     X(256, 128, 8, 16, 16, 1, 1)    \
     X(512, 64, 4, 16, 32, 1, 1)     \
     X(1024, 128, 4, 32, 32, 1, 1)    \
-    X(2048, 128, 1, 16, 8, 16, 1)    \
+    X(2048, 128, 1, 16, 16, 8, 1)    \
     X(4096, 64, 1, 64, 64, 1, 1)    \
     X(8192, 256, 1, 32, 16, 16, 1)   \
     X(16384, 512, 1, 32, 32, 16, 1)  \
