@@ -18,6 +18,7 @@ namespace dsp {
 
 constexpr int kChunk = 32;          // samples between NCO phase checkpoints
 constexpr int kTile = 1024;         // samples per CTA
+constexpr int kDemodOut = 4;        // consecutive outputs per thread of k_demod (kTile = kDemodOut * kThreads)
 constexpr int kThreads = 256;
 constexpr int kTaps = 21, kHist = 20;
 
@@ -59,7 +60,7 @@ struct DemodParams {
 
 __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
 {
-    __shared__ float2 sX[kTile + kHist];
+    __shared__ __align__(16) float2 sX[kTile + kHist + 4];   // (+4: the last thread's 128-bit reads stay inside)
     __shared__ float sCar[kTile + kTile / kChunk];
     __shared__ float sW[kTaps];
     const int tid = threadIdx.x, ch = blockIdx.y;
@@ -89,34 +90,57 @@ __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
     }
     __syncthreads();
     float2 *dst = p.out + (size_t)ch * p.S + t0;
-    for (int i = tid; i < cnt; i += kThreads) {
-        float si, sq;
-        if (p.dofir) {
-            // filter() :385-389 — newest sample first, w[0..20]
-            float oi = 0.0f, oq = 0.0f;
+    // One thread = kDemodOut consecutive outputs (second session of round 2; one output per thread
+    // and 21 shared-memory loads each before): the window of kDemodOut + 20 samples is read once,
+    // 128 bits at a time, and the accumulations run side by side, each in the reference's tap order.
+    constexpr int R = kDemodOut;
+    static_assert(kTile == R * kThreads, "one round per tile");
+    const int i0 = tid * R;
+    if (i0 >= cnt) return;
+    float si[R], sq[R];
+    if (p.dofir) {
+        // filter() :385-389 — newest sample first, w[0..20]
+        float2 x[R + kHist];
+        const float4 *s4 = reinterpret_cast<const float4 *>(sX + i0);     // (sX is 16-byte aligned, i0 a multiple of 4)
 #pragma unroll
-            for (int k = 0; k < kTaps; k++) {
-                float2 x = sX[i + kHist - k];
-                oi = __fadd_rn(oi, __fmul_rn(x.x, sW[k]));
-                oq = __fadd_rn(oq, __fmul_rn(x.y, sW[k]));
-            }
-            si = oi;
-            sq = oq;
-        } else {
-            si = sX[i + kHist].x;
-            sq = sX[i + kHist].y;
+        for (int i = 0; i < (R + kHist) / 2; i++) {
+            const float4 v = s4[i];
+            x[2 * i] = make_float2(v.x, v.y);
+            x[2 * i + 1] = make_float2(v.z, v.w);
         }
+#pragma unroll
+        for (int r = 0; r < R; r++) si[r] = sq[r] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kTaps; k++) {
+            const float w = sW[k];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                si[r] = __fadd_rn(si[r], __fmul_rn(x[r + kHist - k].x, w));
+                sq[r] = __fadd_rn(sq[r], __fmul_rn(x[r + kHist - k].y, w));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            si[r] = sX[i0 + r + kHist].x;
+            sq[r] = sX[i0 + r + kHist].y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = i0 + r;
+        if (i >= cnt) break;
         if (p.dodwn) {
             float car = sCar[(i / kChunk) * (kChunk + 1) + (i % kChunk)];
             double dc, dsn;                                // :425-426 (float)Math.cos(car), (float)Math.sin(car):
             sincos((double)car, &dsn, &dc);                // one argument reduction for both
             float ci = (float)dc;
             float cq = (float)dsn;
-            float a = si, b = sq;
-            si = __fsub_rn(__fmul_rn(a, ci), __fmul_rn(b, cq));   // :432
-            sq = __fadd_rn(__fmul_rn(a, cq), __fmul_rn(b, ci));   // :433
+            float a = si[r], b = sq[r];
+            si[r] = __fsub_rn(__fmul_rn(a, ci), __fmul_rn(b, cq));   // :432
+            sq[r] = __fadd_rn(__fmul_rn(a, cq), __fmul_rn(b, ci));   // :433
         }
-        dst[i] = make_float2(si, sq);
+        dst[i] = make_float2(si[r], sq[r]);
     }
 }
 
