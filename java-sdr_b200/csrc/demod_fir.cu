@@ -488,27 +488,38 @@ __device__ __forceinline__ int java_f2i(float x)
     return (int)x;
 }
 
+// demod.java:451 for the `cnt` samples of a tile (operands in .z) from sample index k0 with the
+// IEEE division itself: the blocks k_detect's running mean does not take through its reciprocal
+// pairs (out of line, so that the common path stays small)
+__device__ __noinline__ float running_mean_div(float avg, const float4 *op, int k0, int cnt)
+{
+    for (int i = 0; i < cnt; i++)
+        avg = __fdiv_rn(__fadd_rn(__fmul_rn((float)(k0 + i), avg), op[i].z), (float)(k0 + i + 1));
+    return avg;
+}
+
 // One CTA per channel.  Pass 1: the detector output of every sample (sample parallel; the FM
 // discriminator's previous sample is the neighbour, or the carried li/lq for the first) and the
 // block maximum of |.| (:448-463).  Pass 2 (AM): the running mean avg = ((k)*avg + x)/(k+1) is a
 // sequential float recurrence (:451), replayed by one thread over tiles staged in shared memory.
 // Pass 3: AM subtracts the mean, AGC scales by 1.0f/max, narrow to s16 as Java's (short) does
 // (:469-473).  `det` is scratch [nchan][S].
-__global__ void __launch_bounds__(256) k_detect(const float2 *__restrict__ mixed, int S, int mode, float fmgain, int doagc,
+__global__ void __launch_bounds__(256, 8) k_detect(const float2 *__restrict__ mixed, int S, int mode, float fmgain, int doagc,
                                                 float2 *__restrict__ lilq, float *__restrict__ det,
                                                 int16_t *__restrict__ audio, float *__restrict__ max_avg)
 {
     __shared__ unsigned s_max;
     __shared__ int s_nan;
     __shared__ float s_avg;
-    __shared__ float s_tile[2048];
-    __shared__ double s_rcp[2048];
+    __shared__ int s_slow;
+    __shared__ __align__(16) float4 s_op[1024];      // per sample of a tile: (y_hi, y_lo, x, x*y_lo), 1/n = y_hi + y_lo
     const int ch = blockIdx.x, tid = threadIdx.x;
     const float2 *x = mixed + (size_t)ch * S;
     float *dv = det + (size_t)ch * S;
     if (tid == 0) {
         s_max = 0u;
         s_nan = 0;
+        s_slow = 0;
         s_avg = 0.0f;
     }
     __syncthreads();
@@ -539,26 +550,60 @@ __global__ void __launch_bounds__(256) k_detect(const float2 *__restrict__ mixed
     if ((mode == MODE_NFM || mode == MODE_WFM) && tid == 0 && S > 0) lilq[ch] = x[S - 1];
     if (mode == MODE_AM) {
         // avg = ((float)k*avg + x) / (float)(k+1) (:451) is a sequential float recurrence with a
-        // division on the chain.  The IEEE quotient of two floats is RN_float(a * RN_double(1/d))
-        // computed in binary64: the product is within 2^-52 (relative) of a/d, and a quotient of two
-        // 24-bit significands cannot come closer than 2^-49 to a rounding boundary of the float
-        // format without being exact (nor sit on one), so the two roundings agree with the single
-        // one.  The reciprocals do not depend on the chain: all threads fill them in per tile, and
-        // the one thread that walks the chain pays FMUL, FADD, F2F, DMUL, F2F per sample (about 45
-        // cycles) instead of the division subroutine (about 110).
-        for (int t0 = 0; t0 < S; t0 += 2048) {
-            const int cnt = min(2048, S - t0);
+        // division on the chain, walked by one thread.  What does not depend on the chain is filled
+        // in per tile by all threads: 1/n as a float pair y_hi + y_lo (relative error < 2^-47) and
+        // x*y_lo.  With t = RN(k*avg) and a = RN(t + x) (the reference's two roundings) the quotient
+        // is q = fma(a, y_hi, p), p = fma(t, y_lo, RN(x*y_lo)): p is a*y_lo to within 3*2^-24 (t and
+        // x are both >= 0 here: amplitudes and their mean), so the value in front of q's rounding is
+        // a/n to within 2^-46 (relative), while a quotient of a 24-bit significand by an integer
+        // n < 2^19 is a float or at least 2^-44 away from every rounding boundary of the float
+        // format (it cannot sit on one: n times a 25-bit midpoint does not fit 24 bits) -- so q is
+        // the IEEE quotient, with FMUL, FADD, FFMA on the chain (13.5 cycles) instead of the division
+        // subroutine (about 110) or a binary64 detour (FMUL, FADD, F2F, DMUL, F2F: about 55).
+        // Range: with every x so far in {0} or [2^-38, 2^64] (the largest finite amplitude is below
+        // 2^64) every sum a is 0 or in [2^-39, 2^85] (three roundings per step over < 2^19 steps
+        // lose less than 12 %), so no product above leaves the normal range by more than a rounding
+        // of y_lo's term, 2^-150 against a/n >= 2^-58.  A block takes the division itself from the
+        // first tile that holds anything else (tiny, infinite, NaN) or reaches n = 2^19.
+        // tests/test_detect_quotient.py checks the arithmetic in exact rationals.
+        for (int t0 = 0; t0 < S; t0 += 1024) {
+            const int cnt = min(1024, S - t0);
+            bool odd = false;
             for (int i = tid; i < cnt; i += blockDim.x) {
-                s_tile[i] = dv[t0 + i];
-                s_rcp[i] = __drcp_rn((double)(t0 + i + 1));
+                const float xv = dv[t0 + i];
+                const double r = __drcp_rn((double)(t0 + i + 1));
+                const float yh = __double2float_rn(r);
+                const float yl = __double2float_rn(__dsub_rn(r, (double)yh));
+                s_op[i] = make_float4(yh, yl, xv, __fmul_rn(xv, yl));
+                odd |= !(xv == 0.0f || (xv >= 3.637978807091713e-12f && xv <= 1.8446744073709552e19f));
             }
+            if (odd || t0 + cnt >= (1 << 19)) s_slow = 1;
             __syncthreads();
             if (tid == 0) {
                 float avg = s_avg;
-#pragma unroll 4
-                for (int i = 0; i < cnt; i++) {
-                    const float a = __fadd_rn(__fmul_rn((float)(t0 + i), avg), s_tile[i]);
-                    avg = __double2float_rn(__dmul_rn((double)a, s_rcp[i]));
+                if (!s_slow) {
+                    float kf = (float)t0;
+                    auto step = [&](const float4 op) {
+                        const float t = __fmul_rn(kf, avg);
+                        const float a = __fadd_rn(t, op.z);
+                        avg = __fmaf_rn(a, op.x, __fmaf_rn(t, op.y, op.w));
+                        kf = __fadd_rn(kf, 1.0f);
+                    };
+                    // two samples per round, the next round's operands fetched ahead of the chain
+                    float4 n0 = s_op[0], n1 = s_op[1];
+                    int i = 0;
+#pragma unroll 2
+                    for (; i + 2 <= cnt; i += 2) {
+                        const float4 c0 = n0, c1 = n1;
+                        const int nx = min(i + 2, 1022);
+                        n0 = s_op[nx];
+                        n1 = s_op[nx + 1];
+                        step(c0);
+                        step(c1);
+                    }
+                    if (i < cnt) step(s_op[i]);
+                } else {
+                    avg = running_mean_div(avg, s_op, t0, cnt);
                 }
                 s_avg = avg;
             }

@@ -34,6 +34,38 @@ def test_demod_audio_bit_exact_without_nco(ctx, mode, doagc):
     d.close()
 
 
+@pytest.mark.parametrize("doagc", [False, True])
+def test_am_running_mean_special_operands(ctx, doagc):
+    """demod.java:451's running mean over the operands the kernel's reciprocal-pair quotient hands
+    to the IEEE division instead (amplitudes below 2^-38, infinities, NaN), zeros, and both sides of
+    that guard; no FIR, no NCO: every s16 sample, max and avg equal to the oracle's."""
+    rate = 96000
+    scales = [0.0, 1e-25, 3e-19, 9e-19, 1e-12, 3e-12, 1e-9, 1.0, 1e15, 1e19, 3e19]
+    nchan = len(scales) + 3
+    rng = np.random.default_rng(451)
+    d = J.demod(ctx, J.AudioDescriptor(rate), nchan=nchan, max_block=9600, dofir=False, dodwn=False)
+    d.set_mode(J.demod.MODE_AM, doagc)
+    lilq = np.zeros(2, np.float32)
+    for n in (9600, 5, 777, 2056, 4100):
+        x = np.empty((nchan, 2 * n), np.float32)
+        for c, sc in enumerate(scales):
+            x[c] = (rng.standard_normal(2 * n) * sc).astype(np.float32)
+        x[len(scales)] = rng.standard_normal(2 * n).astype(np.float32)
+        x[len(scales), : 2 * (n // 2)] = 0.0                     # silence, then signal
+        x[len(scales) + 1] = rng.standard_normal(2 * n).astype(np.float32)
+        x[len(scales) + 1, 2 * (n // 3)] = np.inf                # one infinite sample: avg = inf, then NaN
+        x[len(scales) + 2] = rng.standard_normal(2 * n).astype(np.float32)
+        x[len(scales) + 2, 2 * (n // 2) + 1] = np.nan
+        audio, ma = d.receive_audio(x)
+        for c in range(nchan):
+            o = O.Demod(rate, False, False)
+            with np.errstate(all="ignore"):
+                ref_a, ref_ma = O.demod_detect(o.receive(x[c]), 2, rate, doagc, lilq)
+            assert np.array_equal(audio[c], ref_a), (n, c)
+            assert np.array_equal(ma[c], ref_ma, equal_nan=True), (n, c)
+    d.close()
+
+
 def test_demod_audio_with_nco_within_one_lsb(ctx):
     """With the down-shift on, cos/sin come from different libms: one s16 LSB."""
     rate = 96000

@@ -250,6 +250,45 @@ def other(nchan=1024, S=131072, rate=192000):
     ctx.close()
 
 
+def detect(S=32768, rate=192000):
+    """demod.java's AM detector + running mean + AGC + s16 (:448-481) against the bank width: the
+    running mean is one sequential chain per channel, so the time of a launch is the chain's
+    (S samples) as long as the channels fit the machine in one wave (148 SMs x 8 CTAs)."""
+    import ctypes as C
+    L = J.lib()
+    ctx = J.Context(0)
+    rng = np.random.default_rng(4)
+    adsc = J.AudioDescriptor(rate)
+    tile = rng.uniform(-1, 1, (16, 2 * S)).astype(np.float32)
+    for nchan in (74, 148, 296, 592, 1184, 2368, 4736):
+        d_iq = ctx.dev_alloc(nchan * S * 8)
+        for c0 in range(0, nchan, 16):
+            d_iq.upload(tile[: min(16, nchan - c0)], offset=c0 * S * 8)
+        d_aud = ctx.dev_alloc(nchan * S * 2)
+        d_ma = ctx.dev_alloc(nchan * 8)
+        dm = J.demod(ctx, adsc, nchan=nchan, max_block=S, dofir=False, dodwn=False)
+        for mode, name in ((2, "AM"), (3, "NFM")):
+            dm.set_mode(mode, True)
+            fn = lambda: J._ck(L.jsdr_demod_receive_audio_f32(dm.h, J._ptr(d_iq), S, S, J._ptr(d_aud), J._ptr(d_ma), J.MEM_DEVICE))
+            for _ in range(2):
+                fn()
+            ctx.sync()
+            ctx.profile(True)
+            ctx.profile_read()
+            for _ in range(5):
+                fn()
+            prof = ctx.profile_read()
+            ctx.profile(False)
+            ms = prof["detect"][0] / max(prof["detect"][1], 1)
+            gbs = nchan * S * 10 / ms / 1e6
+            print(f"detect {name:3s} nchan={nchan:5d} S={S}: {ms:8.4f} ms/launch  {1e6 * ms / S:7.2f} ns per sample of a channel  "
+                  f"{gbs:7.1f} GB/s  frac {gbs / PEAK:.3f}", flush=True)
+        dm.close()
+        for b in (d_iq, d_aud, d_ma):
+            b.free()
+    ctx.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mix"
     if what == "mix":
@@ -261,6 +300,8 @@ if __name__ == "__main__":
         chain(*[int(x) for x in sys.argv[2:]])
     elif what == "other":
         other(*[int(x) for x in sys.argv[2:]])
+    elif what == "detect":
+        detect(*[int(x) for x in sys.argv[2:]])
     else:
         fft([int(x) for x in sys.argv[2:]] or [256, 1024, 4096, 9600, 16384, 19200])
 
