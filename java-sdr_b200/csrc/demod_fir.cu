@@ -45,6 +45,74 @@ __global__ void k_car_scout(const float *__restrict__ phi_, float *__restrict__ 
     car_[ch] = car;
 }
 
+// Per-half multiply of an (I, Q) pair (one FMUL2), each half rounded exactly as the scalar
+// __fmul_rn.  The additions that follow stay scalar __fadd_rn on purpose: ptxas contracts a
+// mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 -- with -fmad=false as well, and even when both
+// are written as explicit fma.rn.f32x2 (a*b + -0, then p*1 + c); seen in the SASS -- which would
+// round once where filter() (:385-389) rounds twice.  It leaves FMUL2 + FADD alone
+// (tests/test_abi.py looks for FFMA2 in the built k_demod).
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+
+// (float)Math.sin(car), (float)Math.cos(car) for the NCO (:425-426).  car is a float in [0, 2 pi]
+// (:427-429), so the binary64 sine and cosine need no large-argument path: one Cody-Waite step by
+// k*(pi/2) (k <= 5, the product is exact inside the fma), the two minimax kernels of the classic
+// binary64 libm on [-pi/4, pi/4] (absolute error below 2.3e-16, so the float results differ from a
+// correctly rounded libm's in about one sample in 2^28 and then by one float ulp), quadrant by
+// selects on the rounded floats.  Coefficients sit in constant memory and enter the DFMAs as
+// operands; the library's sincos() spent as many instructions moving its constants into uniform
+// registers and testing for its slow path as on arithmetic.  Arguments beyond |x| <= 8 (never
+// produced by the phase recurrence; NaN) go to the library.
+__constant__ double c_trig[15] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17};
+
+__device__ __noinline__ void nco_sincos_any(float car, float *sn_out, float *cs_out)
+{
+    double ds, dc;
+    sincos((double)car, &ds, &dc);
+    *sn_out = (float)ds;
+    *cs_out = (float)dc;
+}
+
+__device__ __forceinline__ void nco_sincos(float car, float *sn_out, float *cs_out)
+{
+    const double x = (double)car;
+    if (!(fabsf(car) <= 8.0f)) {
+        nco_sincos_any(car, sn_out, cs_out);
+        return;
+    }
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52: nearest integer in the low word
+    const double t = __fma_rn(x, c_trig[12], magic);
+    const int k = __double2loint(t);
+    const double kd = __dsub_rn(t, magic);
+    double r = __fma_rn(-kd, c_trig[13], x);
+    r = __fma_rn(-kd, c_trig[14], r);
+    const double z = __dmul_rn(r, r);
+    double ps = __fma_rn(z, c_trig[5], c_trig[4]);
+    ps = __fma_rn(z, ps, c_trig[3]);
+    ps = __fma_rn(z, ps, c_trig[2]);
+    ps = __fma_rn(z, ps, c_trig[1]);
+    ps = __fma_rn(z, ps, c_trig[0]);
+    const float fs = (float)__fma_rn(__dmul_rn(z, r), ps, r);
+    double pc = __fma_rn(z, c_trig[11], c_trig[10]);
+    pc = __fma_rn(z, pc, c_trig[9]);
+    pc = __fma_rn(z, pc, c_trig[8]);
+    pc = __fma_rn(z, pc, c_trig[7]);
+    pc = __fma_rn(z, pc, c_trig[6]);
+    const float fc = (float)__fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, -0.5, 1.0));
+    const float a = (k & 1) ? fc : fs, b = (k & 1) ? fs : fc;     // sin, cos of r + k*pi/2
+    *sn_out = (k & 2) ? -a : a;
+    *cs_out = ((k + 1) & 2) ? -b : b;
+}
+
 struct DemodParams {
     const float2 *in;
     long long chan_stride;
@@ -99,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
     if (i0 >= cnt) return;
     float si[R], sq[R];
     if (p.dofir) {
-        // filter() :385-389 — newest sample first, w[0..20]
+        // filter() :385-389 — newest sample first, w[0..20]; the two products of a tap as one packed multiply
         float2 x[R + kHist];
         const float4 *s4 = reinterpret_cast<const float4 *>(sX + i0);     // (sX is 16-byte aligned, i0 a multiple of 4)
 #pragma unroll
@@ -113,10 +181,12 @@ __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
 #pragma unroll
         for (int k = 0; k < kTaps; k++) {
             const float w = sW[k];
+            const float2 w2 = make_float2(w, w);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                si[r] = __fadd_rn(si[r], __fmul_rn(x[r + kHist - k].x, w));
-                sq[r] = __fadd_rn(sq[r], __fmul_rn(x[r + kHist - k].y, w));
+                const float2 pr = mul2(x[r + kHist - k], w2);
+                si[r] = __fadd_rn(si[r], pr.x);
+                sq[r] = __fadd_rn(sq[r], pr.y);
             }
         }
     } else {
@@ -132,10 +202,8 @@ __global__ void __launch_bounds__(kThreads) k_demod(const DemodParams p)
         if (i >= cnt) break;
         if (p.dodwn) {
             float car = sCar[(i / kChunk) * (kChunk + 1) + (i % kChunk)];
-            double dc, dsn;                                // :425-426 (float)Math.cos(car), (float)Math.sin(car):
-            sincos((double)car, &dsn, &dc);                // one argument reduction for both
-            float ci = (float)dc;
-            float cq = (float)dsn;
+            float ci, cq;                                  // :425-426 (float)Math.cos(car), (float)Math.sin(car):
+            nco_sincos(car, &cq, &ci);                     // one argument reduction for both
             float a = si[r], b = sq[r];
             si[r] = __fsub_rn(__fmul_rn(a, ci), __fmul_rn(b, cq));   // :432
             sq[r] = __fadd_rn(__fmul_rn(a, cq), __fmul_rn(b, ci));   // :433

@@ -95,3 +95,20 @@ sys.exit(1 if bad else 0)
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(jsdrcuda.__file__)), os.environ.get("PYTHONPATH", "")]))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_demod_fir_multiply_and_add_stay_separately_rounded():
+    """demod.java's filter() (:385-389) rounds the product and the sum of every tap separately.
+    k_demod forms the two products of a tap with one packed multiply; ptxas contracts a packed
+    multiply that feeds a packed add into FFMA2 (one rounding) whatever the flags, so the kernel
+    adds in scalar form -- and this looks at the built library: packed multiplies present, no
+    packed fused multiply-add anywhere in the kernel."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "java-sdr_b200", "libjsdrcuda.so")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4jsdr3dsp7k_demodENS0_11DemodParamsE", so],
+                          capture_output=True, text=True, timeout=300).stdout
+    assert sass.count("FMUL2") >= 21 * 4, "k_demod's packed tap products are missing"
+    assert "FFMA2" not in sass and "FADD2" not in sass
