@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(256, 8) k_detect(const float2 *__restrict__ mi
     __shared__ int s_nan;
     __shared__ float s_avg;
     __shared__ int s_slow;
-    __shared__ __align__(16) float4 s_op[1024];      // per sample of a tile: (y_hi, y_lo, x, x*y_lo), 1/n = y_hi + y_lo
+    __shared__ __align__(16) float4 s_op[2][512];    // per sample of a tile: (y_hi, y_lo, x, x*y_lo), 1/n = y_hi + y_lo; two tiles
     const int ch = blockIdx.x, tid = threadIdx.x;
     const float2 *x = mixed + (size_t)ch * S;
     float *dv = det + (size_t)ch * S;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256, 8) k_detect(const float2 *__restrict__ mi
     if (mode == MODE_AM) {
         // avg = ((float)k*avg + x) / (float)(k+1) (:451) is a sequential float recurrence with a
         // division on the chain, walked by one thread.  What does not depend on the chain is filled
-        // in per tile by all threads: 1/n as a float pair y_hi + y_lo (relative error < 2^-47) and
+        // in per tile by the other threads: 1/n as a float pair y_hi + y_lo (relative error < 2^-47) and
         // x*y_lo.  With t = RN(k*avg) and a = RN(t + x) (the reference's two roundings) the quotient
         // is q = fma(a, y_hi, p), p = fma(t, y_lo, RN(x*y_lo)): p is a*y_lo to within 3*2^-24 (t and
         // x are both >= 0 here: amplitudes and their mean), so the value in front of q's rounding is
@@ -634,44 +634,55 @@ __global__ void __launch_bounds__(256, 8) k_detect(const float2 *__restrict__ mi
         // of y_lo's term, 2^-150 against a/n >= 2^-58.  A block takes the division itself from the
         // first tile that holds anything else (tiny, infinite, NaN) or reaches n = 2^19.
         // tests/test_detect_quotient.py checks the arithmetic in exact rationals.
-        for (int t0 = 0; t0 < S; t0 += 1024) {
-            const int cnt = min(1024, S - t0);
+        // Tiles of 512 samples, two buffers: while thread 0 walks tile t, warps 1..7 fill tile t + 1
+        // (its global loads and binary64 reciprocals stay off the walker's time).  s_slow set by the
+        // fill of tile t + 1 may already be seen by the walk of tile t: both paths give the same bits.
+        constexpr int kT = 512;
+        auto fill = [&](int t0, float4 *buf, int first, int stride) {
+            const int cnt = min(kT, S - t0);
             bool odd = false;
-            for (int i = tid; i < cnt; i += blockDim.x) {
+            for (int i = first; i < cnt; i += stride) {
                 const float xv = dv[t0 + i];
                 const double r = __drcp_rn((double)(t0 + i + 1));
                 const float yh = __double2float_rn(r);
                 const float yl = __double2float_rn(__dsub_rn(r, (double)yh));
-                s_op[i] = make_float4(yh, yl, xv, __fmul_rn(xv, yl));
+                buf[i] = make_float4(yh, yl, xv, __fmul_rn(xv, yl));
                 odd |= !(xv == 0.0f || (xv >= 3.637978807091713e-12f && xv <= 1.8446744073709552e19f));
             }
             if (odd || t0 + cnt >= (1 << 19)) s_slow = 1;
-            __syncthreads();
-            if (tid == 0) {
+        };
+        if (S > 0) fill(0, s_op[0], tid, blockDim.x);
+        __syncthreads();
+        for (int t0 = 0, t = 0; t0 < S; t0 += kT, t++) {
+            const int cnt = min(kT, S - t0);
+            const float4 *cur = s_op[t & 1];
+            if (tid >= 32) {
+                if (t0 + kT < S) fill(t0 + kT, s_op[(t + 1) & 1], tid - 32, blockDim.x - 32);
+            } else if (tid == 0) {
                 float avg = s_avg;
                 if (!s_slow) {
                     float kf = (float)t0;
                     auto step = [&](const float4 op) {
-                        const float t = __fmul_rn(kf, avg);
-                        const float a = __fadd_rn(t, op.z);
-                        avg = __fmaf_rn(a, op.x, __fmaf_rn(t, op.y, op.w));
+                        const float tk = __fmul_rn(kf, avg);
+                        const float a = __fadd_rn(tk, op.z);
+                        avg = __fmaf_rn(a, op.x, __fmaf_rn(tk, op.y, op.w));
                         kf = __fadd_rn(kf, 1.0f);
                     };
                     // two samples per round, the next round's operands fetched ahead of the chain
-                    float4 n0 = s_op[0], n1 = s_op[1];
+                    float4 n0 = cur[0], n1 = cur[1];
                     int i = 0;
 #pragma unroll 2
                     for (; i + 2 <= cnt; i += 2) {
                         const float4 c0 = n0, c1 = n1;
-                        const int nx = min(i + 2, 1022);
-                        n0 = s_op[nx];
-                        n1 = s_op[nx + 1];
+                        const int nx = min(i + 2, kT - 2);
+                        n0 = cur[nx];
+                        n1 = cur[nx + 1];
                         step(c0);
                         step(c1);
                     }
-                    if (i < cnt) step(s_op[i]);
+                    if (i < cnt) step(cur[i]);
                 } else {
-                    avg = running_mean_div(avg, s_op, t0, cnt);
+                    avg = running_mean_div(avg, cur, t0, cnt);
                 }
                 s_avg = avg;
             }
